@@ -1,0 +1,38 @@
+"""b200ivfpq -- B200-native IVF-PQ search engine with the Faiss-style Python surface Chameleon drives.
+
+    import b200ivfpq as faiss
+    index = faiss.index_factory(128, "IVF1024,PQ16")
+    index.train(xt); index.add(xb); index.nprobe = 16
+    D, I = index.search(xq, 10)
+
+Hot path = hand-written sm_100a CUDA kernels behind a C-ABI (include/b200_ivfpq.h); no CPU fallback.
+"""
+from ._lib import LIB_PATH, launch_count, load as load_library
+from .factory import GpuParameterSpace, ParameterSpace, index_factory
+from .index import METRIC_L2, IndexFlatL2, IndexIVFPQ, InvertedLists, ProductQuantizer
+from .io import read_index, write_index
+from .retriever import IndexScanner, LocalB200Retriever
+from .shards import DistributedIndexIVFPQ, merge_shards, shard_index, shard_positions
+
+
+def search_preassigned(index, xq, k, list_ids, coarse_dis=None):
+    """faiss.contrib.ivf_tools.search_preassigned (ralm/server/faiss_server.py:233)."""
+    return index.search_preassigned(xq, k, list_ids)
+
+
+def omp_set_num_threads(n):   # accepted for source compatibility (faiss_retriever.py:79); nothing to set
+    return None
+
+
+def vector_to_array(v):
+    import numpy as np
+    return np.asarray(v)
+
+
+def downcast_index(index):
+    return index
+
+
+__all__ = ["IndexFlatL2", "IndexIVFPQ", "index_factory", "ParameterSpace", "GpuParameterSpace", "search_preassigned",
+           "read_index", "write_index", "LocalB200Retriever", "IndexScanner", "DistributedIndexIVFPQ", "shard_index",
+           "merge_shards", "METRIC_L2", "omp_set_num_threads", "vector_to_array", "downcast_index", "launch_count"]

@@ -1,0 +1,25 @@
+"""Index persistence: the checkpoint/resume role of faiss.write_index / read_index
+(bench_cpu_performance.py:113,164) for this engine, as one .npz of the flat arrays the reference's
+extraction scripts dump (extract_Enzian_U250_required_data.py:222-279, 510-564).
+Reading Faiss's own binary format is listed as "next" (SURVEY.md section 8f, rank 2)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .index import IndexFlatL2, IndexIVFPQ
+
+
+def write_index(index: IndexIVFPQ, fname: str) -> None:
+    a = index.to_arrays() if index.is_trained else {}
+    np.savez(fname if fname.endswith(".npz") else fname + ".npz", d=index.d, nlist=index.nlist, M=index.pq.M,
+             nbits=index.pq.nbits, nprobe=index.nprobe, is_trained=index.is_trained, **a)
+
+
+def read_index(fname: str) -> IndexIVFPQ:
+    z = np.load(fname if fname.endswith(".npz") else fname + ".npz")
+    index = IndexIVFPQ(IndexFlatL2(int(z["d"])), int(z["d"]), int(z["nlist"]), int(z["M"]), int(z["nbits"]))
+    index.nprobe = int(z["nprobe"])
+    if bool(z["is_trained"]):
+        index.set_codebooks(z["coarse"], z["pq"])
+        index.set_lists(z["offsets"], z["codes"], z["ids"])
+    return index

@@ -1,0 +1,92 @@
+"""GPU k-means for index.train (build-time, not on the timed path).
+
+Mirrors what the reference's drivers get from Faiss: Lloyd iterations (niter = 25), training set
+subsampled to at most max_points_per_centroid points per centroid, empty clusters re-seeded by splitting
+the largest one (call sites: bench_cpu_performance.py:98-109, bench_gpu_1bn.py:522-542, 583-594).
+The assignment step is a plain library GEMM (torch.matmul); parity does not depend on it because the
+oracle and the CUDA kernels are always compared on the SAME trained codebooks.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def _assign(x: torch.Tensor, c: torch.Tensor, chunk: int = 1 << 18):
+    """argmin_c ||x - c||^2 via ||c||^2 - 2 x.c ; returns (labels i64, sum of min distances)."""
+    cn = (c * c).sum(1)
+    labels = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    obj = 0.0
+    for i0 in range(0, x.shape[0], chunk):
+        xb = x[i0:i0 + chunk]
+        dist = torch.addmm(cn.unsqueeze(0), xb, c.t(), alpha=-2.0)
+        val, idx = dist.min(dim=1)
+        labels[i0:i0 + chunk] = idx
+        obj += float((val + (xb * xb).sum(1)).sum())
+    return labels, obj
+
+
+def kmeans(x: torch.Tensor, k: int, niter: int = 25, seed: int = 1234, max_points_per_centroid: int = 256,
+           verbose: bool = False) -> torch.Tensor:
+    """x: (n, d) float32 on the GPU.  Returns (k, d) float32 centroids."""
+    assert x.dim() == 2 and x.dtype == torch.float32
+    n, d = x.shape
+    if n < k:
+        raise RuntimeError(f"Number of training points ({n}) should be at least as large as number of clusters ({k})")
+    g = torch.Generator(device=x.device)
+    g.manual_seed(seed)
+    if n > k * max_points_per_centroid:
+        perm = torch.randperm(n, generator=g, device=x.device)[:k * max_points_per_centroid]
+        x = x[perm]
+        n = x.shape[0]
+    perm = torch.randperm(n, generator=g, device=x.device)[:k]
+    c = x[perm].clone()
+    for it in range(niter):
+        labels, obj = _assign(x, c)
+        counts = torch.bincount(labels, minlength=k)
+        sums = torch.zeros_like(c)
+        sums.index_add_(0, labels, x)
+        nonempty = counts > 0
+        c = torch.where(nonempty.unsqueeze(1), sums / counts.clamp(min=1).unsqueeze(1).to(sums.dtype), c)
+        nempty = int((~nonempty).sum())
+        if nempty:
+            # split the largest clusters: empty centroid <- donor * (1 + eps), donor <- donor * (1 - eps)
+            empty_idx = torch.nonzero(~nonempty).flatten()
+            donors = torch.argsort(counts, descending=True)[:nempty]
+            eps = 1.0 / 1024.0
+            c[empty_idx] = c[donors] * (1.0 + eps)
+            c[donors] = c[donors] * (1.0 - eps)
+        if verbose:
+            print(f"  kmeans iter {it}: objective {obj:.6g}, empty {nempty}")
+    return c.contiguous()
+
+
+def kmeans_subspaces(x: torch.Tensor, M: int, ksub: int = 256, niter: int = 25, seed: int = 1234) -> torch.Tensor:
+    """Per-subspace k-means for the product quantizer.  x: (n, d) residuals; returns (M, ksub, dsub)."""
+    n, d = x.shape
+    dsub = d // M
+    xs = x.reshape(n, M, dsub).permute(1, 0, 2).contiguous()          # (M, n, dsub)
+    g = torch.Generator(device=x.device)
+    g.manual_seed(seed)
+    perm = torch.randperm(n, generator=g, device=x.device)[:ksub]
+    c = xs[:, perm, :].clone()                                          # (M, ksub, dsub)
+    ar = torch.arange(M, device=x.device).unsqueeze(1)
+    for _ in range(niter):
+        cn = (c * c).sum(2)                                             # (M, ksub)
+        dist = torch.baddbmm(cn.unsqueeze(1), xs, c.transpose(1, 2), alpha=-2.0)   # (M, n, ksub)
+        labels = dist.argmin(dim=2)                                     # (M, n)
+        flat = (labels + ar * ksub).reshape(-1)
+        counts = torch.bincount(flat, minlength=M * ksub).reshape(M, ksub)
+        sums = torch.zeros(M * ksub, dsub, device=x.device, dtype=x.dtype)
+        sums.index_add_(0, flat, xs.reshape(-1, dsub))
+        sums = sums.reshape(M, ksub, dsub)
+        nonempty = counts > 0
+        c = torch.where(nonempty.unsqueeze(2), sums / counts.clamp(min=1).unsqueeze(2).to(sums.dtype), c)
+        if not bool(nonempty.all()):
+            eps = 1.0 / 1024.0
+            for m in range(M):
+                empty_idx = torch.nonzero(~nonempty[m]).flatten()
+                if empty_idx.numel():
+                    donors = torch.argsort(counts[m], descending=True)[:empty_idx.numel()]
+                    c[m, empty_idx] = c[m, donors] * (1.0 + eps)
+                    c[m, donors] = c[m, donors] * (1.0 - eps)
+    return c.contiguous()

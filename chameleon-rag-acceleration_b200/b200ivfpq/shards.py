@@ -1,0 +1,116 @@
+"""Multi-GPU search: inverted lists sharded by vector, per-shard top-k merged after an all-gather.
+
+Reference behaviour: faiss.index_cpu_to_gpu_multiple(vres, vdev, index, co) with co.shard = True
+(bench_gpu_performance_OSDI.py:586-604), i.e. Faiss IndexShards with the modulo split the reference logs
+("IndexShards shard 0 select modulo 3 = 0", Faiss_experiments/gpu_recall:3-7); the merge is concatenate +
+argsort + take k (bench_multi_cpu_performance_OSDI.py:203-219).
+
+B200 design: one process per GPU (torchrun).  Every rank holds the same codebooks and
+the entries whose position in add order is congruent to its rank; it searches the WHOLE query batch against
+its shard, then one NCCL all-gather of the packed per-shard (D, I) over NVLink and the K5 merge kernel on
+every rank.  No other collective exists on the path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .index import IndexIVFPQ
+
+
+def shard_positions(ntotal: int, rank: int, world: int) -> np.ndarray:
+    """Positions (in add order) owned by `rank`: i % world == rank."""
+    return np.arange(rank, ntotal, world, dtype=np.int64)
+
+
+def shard_index(index: IndexIVFPQ, rank: int, world: int) -> IndexIVFPQ:
+    """Build rank's shard of a populated index (same codebooks, entries with add-order position
+    % world == rank).  Add order is recovered from the stored ids when they are the default sequential
+    ids; for user ids the split is by position inside each list, which balances equally well."""
+    index._finalize_lists()
+    sub = IndexIVFPQ(None, index.d, index.nlist, index.pq.M, index.pq.nbits)
+    sub.set_codebooks(index.quantizer.xb_tensor(), index.pq.centroids_tensor())
+    sub.nprobe = index.nprobe
+    off = index._offsets
+    ntotal = int(off[-1])
+    if ntotal == 0:
+        return sub
+    dev = index._codes.device
+    ids = index._ids
+    seq = bool(torch.equal(torch.sort(ids)[0], torch.arange(ntotal, device=dev)))
+    key = ids if seq else torch.arange(ntotal, device=dev)
+    keep = (key % world) == rank
+    sizes = torch.from_numpy(np.diff(off)).to(dev)
+    list_no = torch.repeat_interleave(torch.arange(index.nlist, device=dev), sizes)
+    counts = torch.bincount(list_no[keep], minlength=index.nlist).cpu().numpy()
+    new_off = np.zeros(index.nlist + 1, np.int64)
+    new_off[1:] = np.cumsum(counts)
+    sub.set_lists(new_off, index._codes[keep].contiguous(), ids[keep].contiguous())
+    return sub
+
+
+def merge_shards(Ds: torch.Tensor, Is: torch.Tensor):
+    """K5 on the current device.  Ds, Is: (nshard, nq, k) CUDA tensors -> (D, I) (nq, k)."""
+    lib = _lib.load()
+    nshard, nq, k = Ds.shape
+    Ds, Is = Ds.contiguous(), Is.contiguous()
+    D = torch.empty((nq, k), dtype=torch.float32, device=Ds.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=Ds.device)
+    with torch.cuda.device(Ds.device):
+        st = int(torch.cuda.current_stream(Ds.device).cuda_stream)
+        _lib.check(lib.b200_ivfpq_merge_shards(nshard, nq, k, Ds.data_ptr(), Is.data_ptr(), D.data_ptr(), I.data_ptr(),
+                                               st))
+    return D, I
+
+
+def pack_results(D: torch.Tensor, I: torch.Tensor) -> torch.Tensor:
+    """(nq, k) f32 + (nq, k) i64 -> one (nq, k, 3) int32 buffer so that the exchange is a single all-gather."""
+    out = torch.empty(D.shape + (3,), dtype=torch.int32, device=D.device)
+    out[..., 0] = D.view(torch.int32)
+    out[..., 1:] = I.view(torch.int32).reshape(I.shape + (2,))
+    return out
+
+
+def unpack_results(buf: torch.Tensor):
+    D = buf[..., 0].contiguous().view(torch.float32)
+    I = buf[..., 1:].contiguous().view(torch.int64).reshape(buf.shape[:-1])
+    return D, I
+
+
+class DistributedIndexIVFPQ:
+    """The rank-local view of a sharded index.  search() = local search -> all_gather -> merge.
+
+    `merge_fn` / `local_search_fn` are injection points for the CPU (gloo) tests of the exchange logic;
+    the product path uses the CUDA kernels."""
+
+    def __init__(self, local_index, group=None, merge_fn=None, local_search_fn=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.local = local_index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._merge = merge_fn or merge_shards
+        self._local_search = local_search_fn or (lambda xq, k: self.local.search(xq, k))
+        self.d = getattr(local_index, "d", None)
+
+    @property
+    def nprobe(self):
+        return self.local.nprobe
+
+    @nprobe.setter
+    def nprobe(self, v):
+        self.local.nprobe = v
+
+    def search(self, xq: torch.Tensor, k: int):
+        D, I = self._local_search(xq, k)
+        if self.world == 1:
+            return D, I
+        mine = pack_results(D, I)
+        gathered = torch.empty((self.world,) + mine.shape, dtype=mine.dtype, device=mine.device)
+        self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        Ds, Is = unpack_results(gathered)
+        return self._merge(Ds, Is)

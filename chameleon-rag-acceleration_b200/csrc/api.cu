@@ -1,0 +1,501 @@
+// api.cu -- C-ABI (include/b200_ivfpq.h) and host-side orchestration of the search path.
+// One index handle owns only its workspace; codebooks and inverted lists are borrowed device pointers
+// (torch tensors on the Python side), so a populated index costs no extra HBM.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_ivfpq.h"
+#include "kernels.cuh"
+#include "scan_skew.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t err__ = (expr);                                                                 \
+        if (err__ != cudaSuccess)                                                                   \
+            return fail(B200_IVFPQ_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+#define LAUNCH_CHECK()                 \
+    do {                               \
+        g_launches.fetch_add(1);       \
+        CUDA_TRY(cudaGetLastError());  \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B200_IVFPQ_ENOMEM, "workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+constexpr size_t kCoarseMatrixBudget = size_t(1) << 30;   // bytes of coarse distances per query chunk
+constexpr size_t kPairOutBudget = size_t(2) << 30;        // bytes of per-pair candidates per query chunk
+
+}  // namespace
+
+struct b200_ivfpq_index {
+    int d = 0, M = 0, nbits = 8, dsub = 0;
+    int64_t nlist = 0, ntotal = 0;
+    const float* cent = nullptr;
+    const float* pq = nullptr;
+    const uint8_t* codes = nullptr;
+    const int64_t* ids = nullptr;
+    bool has_lists = false;
+    int device = 0, num_sms = 148;
+    int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free)
+    // workspace
+    DevBuf offsets, coarse_mat, probe32, hist, start, order, out_keys, out_cnt, qthr, stats, pq_t;
+    DevBuf host_xq, host_D, host_I, tmp_list_no;
+    // instrumentation
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    bool stage_valid = false;
+    cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+int ensure_events(b200_ivfpq_index* h) {
+    for (auto& e : h->ev)
+        if (!e) CUDA_TRY(cudaEventCreate(&e));
+    return 0;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+int grid1d(int64_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
+
+// K1 for one chunk of queries: distances to all centroids, then nprobe-select.
+int run_coarse(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int nprobe, int32_t* probe32, int64_t* ids64,
+               float* dis, cudaStream_t st, bool time_stages) {
+    int rc = h->coarse_mat.ensure(sizeof(float) * nq * h->nlist);
+    if (rc) return rc;
+    dim3 grid(static_cast<unsigned>((h->nlist + kCoarseTile - 1) / kCoarseTile),
+              static_cast<unsigned>((nq + kCoarseTile - 1) / kCoarseTile));
+    coarse_dist_kernel<<<grid, kThreads, 0, st>>>(d_xq, h->cent, h->coarse_mat.as<float>(), (int)nq, h->nlist, h->d,
+                                                  h->nlist);
+    LAUNCH_CHECK();
+    if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    size_t smem = TopK::smem_bytes(nprobe, kSelCap);
+    rc = set_smem(coarse_select_kernel, smem);
+    if (rc) return rc;
+    coarse_select_kernel<<<(unsigned)nq, kThreads, smem, st>>>(h->coarse_mat.as<float>(), h->nlist, h->nlist, nprobe,
+                                                              probe32, ids64, dis);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t coarse_chunk(const b200_ivfpq_index* h) {
+    int64_t qb = static_cast<int64_t>(kCoarseMatrixBudget / (sizeof(float) * h->nlist));
+    qb = (qb / kCoarseTile) * kCoarseTile;
+    return qb < kCoarseTile ? kCoarseTile : qb;
+}
+
+template <int VEC>
+int launch_scan(b200_ivfpq_index* h, const ScanParams& sp, int64_t npairs, cudaStream_t st) {
+    size_t smem = scan_smem_bytes(sp.M, sp.d, sp.k);
+    int rc = set_smem(scan_pairs_kernel<VEC>, smem);
+    if (rc) return rc;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_pairs_kernel<VEC>, kThreads, smem));
+    if (per_sm < 1) return fail(B200_IVFPQ_EUNSUPPORTED, "scan kernel does not fit (smem %zu B)", smem);
+    int64_t grid = static_cast<int64_t>(per_sm) * h->num_sms;
+    if (grid > npairs) grid = npairs;
+    scan_pairs_kernel<VEC><<<(unsigned)grid, kThreads, smem, st>>>(sp);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int nprobe, const int64_t* d_list_ids,
+                float* d_D, int64_t* d_I, cudaStream_t st) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!h->cent || !h->pq) return fail(B200_IVFPQ_ESTATE, "index is not trained (set_codebooks not called)");
+    if (!h->has_lists) return fail(B200_IVFPQ_ESTATE, "inverted lists not set (set_lists not called)");
+    if (nq < 0) return fail(B200_IVFPQ_EINVAL, "nq = %lld < 0", (long long)nq);
+    if (k < 1 || k > B200_IVFPQ_MAX_K) return fail(B200_IVFPQ_EINVAL, "k = %d out of [1, %d]", k, B200_IVFPQ_MAX_K);
+    if (nprobe < 1 || nprobe > B200_IVFPQ_MAX_NPROBE)
+        return fail(B200_IVFPQ_EINVAL, "nprobe = %d out of [1, %d]", nprobe, B200_IVFPQ_MAX_NPROBE);
+    if (nq == 0) return 0;
+    if (!d_xq || !d_D || !d_I) return fail(B200_IVFPQ_EINVAL, "null query / result pointer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!d_list_ids && nprobe > h->nlist) nprobe = static_cast<int>(h->nlist);   // Faiss clamps nprobe to nlist
+
+    const bool timing = h->timing;
+    if (timing) {
+        int rc = ensure_events(h);
+        if (rc) return rc;
+    }
+    h->stage_valid = false;
+    h->last_stream = st;
+
+    // query chunking keeps the workspace bounded
+    int64_t qb = nq;
+    if (!d_list_ids) qb = std::min<int64_t>(qb, coarse_chunk(h));
+    qb = std::min<int64_t>(qb, std::max<int64_t>(1, (int64_t)(kPairOutBudget / (sizeof(uint64_t) * (size_t)nprobe * k))));
+    qb = std::min<int64_t>(qb, (int64_t)((1ll << 30) / nprobe));
+    const bool single_chunk = qb >= nq;
+
+    int rc;
+    if ((rc = h->stats.ensure(sizeof(PairStats)))) return rc;
+    if ((rc = h->probe32.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
+    if ((rc = h->hist.ensure(sizeof(int) * h->nlist))) return rc;
+    if ((rc = h->start.ensure(sizeof(int) * h->nlist))) return rc;
+    if ((rc = h->order.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
+    if ((rc = h->out_keys.ensure(sizeof(uint64_t) * qb * nprobe * k))) return rc;
+    if ((rc = h->out_cnt.ensure(sizeof(int) * qb * nprobe))) return rc;
+    if ((rc = h->qthr.ensure(sizeof(uint32_t) * qb))) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->stats.p, 0, sizeof(PairStats), st));
+
+    for (int64_t q0 = 0; q0 < nq; q0 += qb) {
+        const int64_t nqc = std::min<int64_t>(qb, nq - q0);
+        const int64_t npairs = nqc * nprobe;
+        const float* xq = d_xq + q0 * h->d;
+        const bool tm = timing && single_chunk;
+        int32_t* probe32 = h->probe32.as<int32_t>();
+
+        if (tm) CUDA_TRY(cudaEventRecord(h->ev[0], st));
+        if (d_list_ids) {
+            probes_from_i64_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(d_list_ids + q0 * nprobe, probe32, npairs,
+                                                                       h->nlist);
+            LAUNCH_CHECK();
+            if (tm) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+        } else {
+            if ((rc = run_coarse(h, nqc, xq, nprobe, probe32, nullptr, nullptr, st, tm))) return rc;
+        }
+        if (tm) CUDA_TRY(cudaEventRecord(h->ev[2], st));
+
+        // pair setup
+        CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * h->nlist, st));
+        CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs, st));
+        fill_u32_kernel<<<grid1d(nqc, 256), 256, 0, st>>>(h->qthr.as<uint32_t>(), nqc, kInfBits);
+        LAUNCH_CHECK();
+        PairStats* stats = h->stats.as<PairStats>();
+        pair_hist_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
+                                                             h->hist.as<int>(), stats);
+        LAUNCH_CHECK();
+        pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->nlist, stats);
+        LAUNCH_CHECK();
+        pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
+                                                                h->start.as<int>(), h->order.as<int32_t>());
+        LAUNCH_CHECK();
+        if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));
+
+        // K2+K3+K4
+        ScanParams sp;
+        sp.xq = xq;
+        sp.cent = h->cent;
+        sp.pq = h->pq;
+        sp.offsets = h->offsets.as<int64_t>();
+        sp.codes = h->codes;
+        sp.probe = probe32;
+        sp.order = h->order.as<int32_t>();
+        sp.out_keys = h->out_keys.as<uint64_t>();
+        sp.out_cnt = h->out_cnt.as<int>();
+        sp.qthr = h->qthr.as<uint32_t>();
+        sp.stats = stats;
+        sp.d = h->d;
+        sp.M = h->M;
+        sp.dsub = h->dsub;
+        sp.nprobe = nprobe;
+        sp.k = k;
+        const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
+        bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
+        if (h->scan_variant == 2 && !use_skew)
+            return fail(B200_IVFPQ_EUNSUPPORTED, "skewed scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
+        if (use_skew) {
+            if ((rc = launch_scan_skew(sp, h->pq_t.as<float>(), npairs, h->num_sms, st))) {
+                if (rc == -1) return fail(B200_IVFPQ_ECUDA, "skewed scan launch failed: %s",
+                                          cudaGetErrorString(cudaGetLastError()));
+                return rc;
+            }
+            g_launches.fetch_add(1);
+        } else if (h->M % 16 == 0 && aligned16) {
+            if ((rc = launch_scan<16>(h, sp, npairs, st))) return rc;
+        } else if (h->M % 8 == 0 && (reinterpret_cast<uintptr_t>(h->codes) & 7) == 0) {
+            if ((rc = launch_scan<8>(h, sp, npairs, st))) return rc;
+        } else if (h->M % 4 == 0 && (reinterpret_cast<uintptr_t>(h->codes) & 3) == 0) {
+            if ((rc = launch_scan<4>(h, sp, npairs, st))) return rc;
+        } else {
+            if ((rc = launch_scan<1>(h, sp, npairs, st))) return rc;
+        }
+        if (tm) CUDA_TRY(cudaEventRecord(h->ev[4], st));
+
+        // K4b
+        size_t msmem = TopK::smem_bytes(k, kMergeCap);
+        if ((rc = set_smem(merge_query_kernel, msmem))) return rc;
+        merge_query_kernel<<<(unsigned)nqc, kThreads, msmem, st>>>(h->out_keys.as<uint64_t>(), h->out_cnt.as<int>(),
+                                                                  probe32, h->offsets.as<int64_t>(), h->ids, nprobe, k,
+                                                                  d_D + q0 * k, d_I + q0 * k);
+        LAUNCH_CHECK();
+        if (tm) {
+            CUDA_TRY(cudaEventRecord(h->ev[5], st));
+            h->stage_valid = true;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b200_ivfpq_last_error(void) { return g_last_error.c_str(); }
+
+const char* b200_ivfpq_version(void) { return "b200-ivfpq 0.1 (sm_100a)"; }
+
+int64_t b200_ivfpq_launch_count(void) { return g_launches.load(); }
+
+int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out) {
+    if (!out) return fail(B200_IVFPQ_EINVAL, "out == NULL");
+    *out = nullptr;
+    if (d <= 0 || nlist <= 0 || m <= 0) return fail(B200_IVFPQ_EINVAL, "d, nlist and m must be positive");
+    if (nbits != 8) return fail(B200_IVFPQ_EUNSUPPORTED, "nbits = %d: only 8-bit PQ codes are supported", nbits);
+    if (d % m != 0) return fail(B200_IVFPQ_EINVAL, "d = %d is not a multiple of m = %d", d, m);
+    if (nlist >= (int64_t(1) << 31)) return fail(B200_IVFPQ_EINVAL, "nlist too large");
+    if (m > 256) return fail(B200_IVFPQ_EUNSUPPORTED, "m = %d > 256", m);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B200_IVFPQ_ECUDA, "no CUDA device available (%s): this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    b200_ivfpq_index* h = new b200_ivfpq_index();
+    h->d = d;
+    h->nlist = nlist;
+    h->M = m;
+    h->nbits = nbits;
+    h->dsub = d / m;
+    CUDA_TRY(cudaGetDevice(&h->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    const char* v = getenv("B200_IVFPQ_SCAN");
+    if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : 0;
+    *out = h;
+    return 0;
+}
+
+int b200_ivfpq_destroy(b200_ivfpq_t h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t,
+                      &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
+                      &h->host_D,  &h->host_I,     &h->tmp_list_no};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    delete h;
+    return 0;
+}
+
+int b200_ivfpq_set_codebooks(b200_ivfpq_t h, const float* d_centroids, const float* d_pq) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!d_centroids) return fail(B200_IVFPQ_EINVAL, "null centroid pointer");
+    h->cent = d_centroids;
+    h->pq = d_pq;
+    if (!d_pq) return 0;   // coarse-only handle (IndexFlatL2): b200_ivfpq_coarse works, search does not
+    // m-fastest copy of the PQ codebook for the conflict-free scan kernel's LUT build
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int64_t total = static_cast<int64_t>(h->M) * 256 * h->dsub;
+    int rc = h->pq_t.ensure(sizeof(float) * total);
+    if (rc) return rc;
+    pq_transpose_kernel<<<grid1d(total, 256), 256>>>(d_pq, h->pq_t.as<float>(), h->M, h->dsub);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, const uint8_t* d_codes, const int64_t* d_ids,
+                         int64_t ntotal) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!h_offsets) return fail(B200_IVFPQ_EINVAL, "null offsets");
+    if (ntotal < 0 || h_offsets[0] != 0 || h_offsets[h->nlist] != ntotal)
+        return fail(B200_IVFPQ_EINVAL, "offsets must start at 0 and end at ntotal");
+    for (int64_t l = 0; l < h->nlist; l++) {
+        int64_t sz = h_offsets[l + 1] - h_offsets[l];
+        if (sz < 0) return fail(B200_IVFPQ_EINVAL, "offsets not monotone at list %lld", (long long)l);
+        if (sz >= (int64_t(1) << 32)) return fail(B200_IVFPQ_EUNSUPPORTED, "list %lld longer than 2^32", (long long)l);
+    }
+    if (ntotal > 0 && !d_codes) return fail(B200_IVFPQ_EINVAL, "null codes with ntotal > 0");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = h->offsets.ensure(sizeof(int64_t) * (h->nlist + 1));
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(h->offsets.p, h_offsets, sizeof(int64_t) * (h->nlist + 1), cudaMemcpyHostToDevice));
+    h->codes = d_codes;
+    h->ids = d_ids;
+    h->ntotal = ntotal;
+    h->has_lists = true;
+    return 0;
+}
+
+int b200_ivfpq_coarse(b200_ivfpq_t h, int64_t nq, const float* d_xq, int nprobe, int64_t* d_ids, float* d_dis,
+                      void* stream) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!h->cent) return fail(B200_IVFPQ_ESTATE, "index is not trained (set_codebooks not called)");
+    if (nprobe < 1 || nprobe > B200_IVFPQ_MAX_NPROBE)
+        return fail(B200_IVFPQ_EINVAL, "nprobe = %d out of [1, %d]", nprobe, B200_IVFPQ_MAX_NPROBE);
+    if (nq < 0) return fail(B200_IVFPQ_EINVAL, "nq < 0");
+    if (nq == 0) return 0;
+    if (!d_xq || !d_ids) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t qb = coarse_chunk(h);
+    for (int64_t q0 = 0; q0 < nq; q0 += qb) {
+        int64_t nqc = std::min<int64_t>(qb, nq - q0);
+        int rc = run_coarse(h, nqc, d_xq + q0 * h->d, nprobe, nullptr, d_ids + q0 * nprobe,
+                            d_dis ? d_dis + q0 * nprobe : nullptr, st, false);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int b200_ivfpq_search(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe, float* d_D, int64_t* d_I,
+                      void* stream) {
+    return search_impl(h, nq, d_xq, k, nprobe, nullptr, d_D, d_I, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_ivfpq_search_preassigned(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe,
+                                  const int64_t* d_list_ids, float* d_D, int64_t* d_I, void* stream) {
+    if (!d_list_ids) return fail(B200_IVFPQ_EINVAL, "null list ids");
+    return search_impl(h, nq, d_xq, k, nprobe, d_list_ids, d_D, d_I, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_ivfpq_search_host(b200_ivfpq_t h, int64_t nq, const float* h_xq, int k, int nprobe, float* h_D,
+                           int64_t* h_I) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (nq < 0) return fail(B200_IVFPQ_EINVAL, "nq < 0");
+    if (nq == 0) return 0;
+    if (!h_xq || !h_D || !h_I) return fail(B200_IVFPQ_EINVAL, "null host pointer");
+    if (k < 1 || k > B200_IVFPQ_MAX_K) return fail(B200_IVFPQ_EINVAL, "k = %d out of [1, %d]", k, B200_IVFPQ_MAX_K);
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = h->host_xq.ensure(sizeof(float) * nq * h->d))) return rc;
+    if ((rc = h->host_D.ensure(sizeof(float) * nq * k))) return rc;
+    if ((rc = h->host_I.ensure(sizeof(int64_t) * nq * k))) return rc;
+    cudaStream_t st = nullptr;
+    CUDA_TRY(cudaMemcpyAsync(h->host_xq.p, h_xq, sizeof(float) * nq * h->d, cudaMemcpyHostToDevice, st));
+    rc = search_impl(h, nq, h->host_xq.as<float>(), k, nprobe, nullptr, h->host_D.as<float>(), h->host_I.as<int64_t>(),
+                     st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_D, h->host_D.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_I, h->host_I.p, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200_ivfpq_assign_encode(b200_ivfpq_t h, int64_t n, const float* d_x, int64_t* d_list_no, uint8_t* d_codes,
+                             void* stream) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!h->cent || !h->pq) return fail(B200_IVFPQ_ESTATE, "index is not trained (set_codebooks not called)");
+    if (n < 0) return fail(B200_IVFPQ_EINVAL, "n < 0");
+    if (n == 0) return 0;
+    if (!d_x || !d_list_no) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t qb = coarse_chunk(h);
+    for (int64_t q0 = 0; q0 < n; q0 += qb) {
+        int64_t nqc = std::min<int64_t>(qb, n - q0);
+        int rc = run_coarse(h, nqc, d_x + q0 * h->d, 1, nullptr, d_list_no + q0, nullptr, st, false);
+        if (rc) return rc;
+    }
+    if (d_codes) {
+        size_t smem = sizeof(float) * (256 * (size_t)h->dsub + (size_t)h->dsub * kThreads);
+        int rc = set_smem(encode_kernel, smem);
+        if (rc) return rc;
+        dim3 grid(static_cast<unsigned>((n + kThreads - 1) / kThreads), static_cast<unsigned>(h->M));
+        encode_kernel<<<grid, kThreads, smem, st>>>(d_x, h->cent, d_list_no, h->pq, n, h->d, h->M, h->dsub, d_codes);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int b200_ivfpq_merge_shards(int nshard, int64_t nq, int k, const float* d_Ds, const int64_t* d_Is, float* d_D,
+                            int64_t* d_I, void* stream) {
+    if (nshard < 1 || nq < 0) return fail(B200_IVFPQ_EINVAL, "bad nshard / nq");
+    if (k < 1 || k > B200_IVFPQ_MAX_K) return fail(B200_IVFPQ_EINVAL, "k = %d out of [1, %d]", k, B200_IVFPQ_MAX_K);
+    if ((int64_t)nshard * k >= (int64_t(1) << 31)) return fail(B200_IVFPQ_EINVAL, "nshard * k too large");
+    if (nq == 0) return 0;
+    if (!d_Ds || !d_Is || !d_D || !d_I) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    size_t smem = TopK::smem_bytes(k, kMergeCap);
+    int rc = set_smem(merge_shards_kernel, smem);
+    if (rc) return rc;
+    merge_shards_kernel<<<(unsigned)nq, kThreads, smem, st>>>(d_Ds, d_Is, nshard, nq, k, d_D, d_I);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200_ivfpq_set_stage_timing(b200_ivfpq_t h, int enable) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    h->timing = enable != 0;
+    return 0;
+}
+
+int b200_ivfpq_get_stage_ms(b200_ivfpq_t h, float* h_ms5) {
+    if (!h || !h_ms5) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    if (!h->stage_valid) return fail(B200_IVFPQ_ESTATE, "no timed single-chunk search recorded");
+    CUDA_TRY(cudaEventSynchronize(h->ev[5]));
+    for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventElapsedTime(&h_ms5[i], h->ev[i], h->ev[i + 1]));
+    return 0;
+}
+
+int b200_ivfpq_get_last_scan_stats(b200_ivfpq_t h, int64_t* h_bytes, int64_t* h_codes) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!h->stats.p) return fail(B200_IVFPQ_ESTATE, "no search recorded");
+    CUDA_TRY(cudaStreamSynchronize(h->last_stream));
+    PairStats s;
+    CUDA_TRY(cudaMemcpy(&s, h->stats.p, sizeof(s), cudaMemcpyDeviceToHost));
+    if (h_codes) *h_codes = static_cast<int64_t>(s.scan_codes);
+    if (h_bytes) *h_bytes = static_cast<int64_t>(s.scan_codes) * h->M;
+    return 0;
+}
+
+}  // extern "C"

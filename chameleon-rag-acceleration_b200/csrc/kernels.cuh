@@ -1,0 +1,554 @@
+// kernels.cuh -- sm_100a kernels of the IVF-PQ search path.
+//
+//   K1  coarse_dist_kernel / coarse_select_kernel   a1  exact fp32 query x centroid L2^2, nprobe-select
+//   K2+K3+K4  scan_pairs_kernel                      a2-a5 residual, LUT in shared memory, ADC scan, top-k
+//   K4b merge_query_kernel                           a5,a6 per-query merge over probes + id lookup
+//   K5  merge_shards_kernel                          multi-GPU merge after the all-gather
+//   encode_kernel                                    a9  PQ encode of residuals for index.add
+//
+// Arithmetic follows the oracle contract bit for bit: every multiply/add is a separately rounded fp32
+// op (__fsub_rn/__fmul_rn/__fadd_rn are never contracted into FMA) and every accumulation runs in the
+// oracle's order (j ascending, m ascending).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "topk.cuh"
+
+namespace b200 {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float sqdiff_acc(float acc, float a, float b) {
+    float diff = __fsub_rn(a, b);
+    return __fadd_rn(acc, __fmul_rn(diff, diff));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a: exact coarse distances.  out[q][c] = sum_j (xq[q][j] - cent[c][j])^2, j ascending.
+// 64 x 64 tile per CTA, 4 x 4 per thread, operands staged through shared memory in k-chunks.
+// Reference: IVFPQ_1B_search.ipynb:7922-7927, 7991-7996 (distance to every centroid).
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoarseTile = 64;
+constexpr int kCoarseKC = 16;
+
+__global__ void __launch_bounds__(kThreads) coarse_dist_kernel(const float* __restrict__ xq,
+                                                               const float* __restrict__ cent,
+                                                               float* __restrict__ out, int nq, int64_t nlist,
+                                                               int d, int64_t out_stride) {
+    __shared__ __align__(16) float sQ[kCoarseKC][kCoarseTile + 4];
+    __shared__ __align__(16) float sC[kCoarseKC][kCoarseTile + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t cbase = static_cast<int64_t>(blockIdx.x) * kCoarseTile;
+    const int qbase = blockIdx.y * kCoarseTile;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < d; k0 += kCoarseKC) {
+        const int kc = min(kCoarseKC, d - k0);
+#pragma unroll
+        for (int i = 0; i < (kCoarseTile * kCoarseKC) / kThreads; i++) {
+            int e = tid + i * kThreads;
+            int row = e / kCoarseKC, col = e % kCoarseKC;
+            float qv = 0.0f, cv = 0.0f;
+            if (col < kc) {
+                if (qbase + row < nq) qv = xq[static_cast<int64_t>(qbase + row) * d + k0 + col];
+                if (cbase + row < nlist) cv = cent[(cbase + row) * d + k0 + col];
+            }
+            sQ[col][row] = qv;
+            sC[col][row] = cv;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < kc; kk++) {
+            float4 qa = *reinterpret_cast<const float4*>(&sQ[kk][ty * 4]);
+            float4 cb = *reinterpret_cast<const float4*>(&sC[kk][tx * 4]);
+            float qv[4] = {qa.x, qa.y, qa.z, qa.w};
+            float cv[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = sqdiff_acc(acc[i][j], qv[i], cv[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int q = qbase + ty * 4 + i;
+        if (q >= nq) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t c = cbase + tx * 4 + j;
+            if (c < nlist) out[static_cast<int64_t>(q) * out_stride + c] = acc[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b: per-query nprobe-select over a row of coarse distances.  One CTA per query.
+// Output ascending by (distance, centroid id) -- "sort, take nprobe" (ipynb:7997-7999).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelCap = 2048;
+constexpr int kSelTile = kThreads * 4;
+
+__global__ void __launch_bounds__(kThreads) coarse_select_kernel(const float* __restrict__ dist, int64_t nlist,
+                                                                 int64_t stride, int nprobe,
+                                                                 int32_t* __restrict__ probe32,
+                                                                 int64_t* __restrict__ ids64,
+                                                                 float* __restrict__ dis_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TopK tk;
+    tk.bind(smem_raw, nprobe, kSelCap);
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const float* row = dist + q * stride;
+    if (tid == 0) tk.reset(kInfBits);
+    __syncthreads();
+    uint32_t thr = kInfBits;
+    for (int64_t base = 0; base < nlist; base += kSelTile) {
+#pragma unroll
+        for (int u = 0; u < kSelTile / kThreads; u++) {
+            int64_t c = base + u * kThreads + tid;
+            uint32_t bits = 0xffffffffu;
+            if (c < nlist) bits = __float_as_uint(row[c]);
+            tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
+        }
+        __syncthreads();
+        if (tk.pending() > kSelCap - kSelTile) tk.flush<kThreads>(kInfBits);
+        thr = tk.threshold();
+    }
+    __syncthreads();
+    tk.flush<kThreads>(kInfBits);
+    const int nb = tk.count();
+    const uint64_t* s = tk.sorted();
+    for (int i = tid; i < nprobe; i += kThreads) {
+        int32_t id = -1;
+        float dv = FLT_MAX;
+        if (i < nb) {
+            id = static_cast<int32_t>(s[i] & 0xffffffffu);
+            dv = __uint_as_float(static_cast<uint32_t>(s[i] >> 32));
+        }
+        if (probe32) probe32[q * nprobe + i] = id;
+        if (ids64) ids64[q * nprobe + i] = id;
+        if (dis_out) dis_out[q * nprobe + i] = dv;
+    }
+}
+
+// convert caller-provided int64 list ids (search_preassigned) to the internal int32 probe table
+__global__ void probes_from_i64_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
+                                       int64_t nlist) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int64_t v = in[i];
+        out[i] = (v >= 0 && v < nlist) ? static_cast<int32_t>(v) : -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair setup: order the (query, probe) pairs by list id so that CTAs scanning the same list run
+// back to back and its codes are served from L2 after the first touch.  Counting sort in three tiny
+// kernels; also accumulates the algorithmic scan statistics the roofline uses.
+// ------------------------------------------------------------------------------------------------
+struct PairStats {
+    unsigned long long scan_codes;   // sum over valid pairs of list_size
+    int nvalid;                      // number of pairs with a non-empty list
+    int work_counter;                // dynamic scheduler of scan_pairs_kernel
+};
+
+__global__ void pair_hist_kernel(const int32_t* __restrict__ probe, int64_t npairs,
+                                 const int64_t* __restrict__ offsets, int* __restrict__ hist,
+                                 PairStats* __restrict__ stats) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    unsigned long long codes = 0;
+    if (i < npairs) {
+        int l = probe[i];
+        if (l >= 0) {
+            int64_t sz = offsets[l + 1] - offsets[l];
+            if (sz > 0) {
+                atomicAdd(&hist[l], 1);
+                codes = static_cast<unsigned long long>(sz);
+            }
+        }
+    }
+    // warp-reduce then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) codes += __shfl_down_sync(0xffffffffu, codes, o);
+    if ((threadIdx.x & 31) == 0 && codes) atomicAdd(&stats->scan_codes, codes);
+}
+
+// exclusive scan of hist[nlist] -> start[nlist]; single CTA (nlist <= a few 100k)
+__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ hist, int* __restrict__ start,
+                                                         int64_t nlist, PairStats* __restrict__ stats) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nlist; base += 1024) {
+        int64_t i = base + tid;
+        int v = i < nlist ? hist[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        int prefix = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
+        if (i < nlist) start[i] = prefix;
+        __syncthreads();
+        if (tid == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        stats->nvalid = carry;
+        stats->work_counter = 0;
+    }
+}
+
+__global__ void pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t npairs,
+                                    const int64_t* __restrict__ offsets, int* __restrict__ cursor,
+                                    int32_t* __restrict__ order) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    int l = probe[i];
+    if (l < 0) return;
+    if (offsets[l + 1] - offsets[l] <= 0) return;
+    int pos = atomicAdd(&cursor[l], 1);
+    order[pos] = static_cast<int32_t>(i);
+}
+
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t v) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2+K3+K4: one CTA per (query, probe) pair, persistent CTAs pulling pairs from a work counter.
+//   a2 residual  r = q - c                                   (ipynb:8006, LUT_construction.hpp:182-187)
+//   a3 LUT       T[m][k] = sum_j (r[m*dsub+j] - pq[m][k][j])^2 in shared memory
+//                                                            (ipynb:7929-7946, LUT_construction.hpp:189-209)
+//   a4 ADC       dist = sum_m T[m][code[m]], m ascending       (ipynb:7948-7960, ADC.hpp:88-91)
+//   a5 top-k     exact, (distance, offset) order, per pair    (ipynb:7980-7982)
+// Generic in M (any M with d % M == 0); codes are read straight from HBM/L2 into registers with the
+// widest aligned vector load M allows (VEC bytes).  A per-query global threshold (the best known k-th
+// distance over the probes finished so far) prunes candidates across the probes of a query.
+// ------------------------------------------------------------------------------------------------
+struct ScanParams {
+    const float* xq;          // (nq, d)
+    const float* cent;        // (nlist, d)
+    const float* pq;          // (M, 256, dsub)
+    const int64_t* offsets;   // (nlist + 1)
+    const uint8_t* codes;     // (ntotal, M)
+    const int32_t* probe;     // (nq * nprobe) list id or -1
+    const int32_t* order;     // (nvalid) pair indices sorted by list
+    uint64_t* out_keys;       // (nq * nprobe, k)
+    int* out_cnt;             // (nq * nprobe), pre-zeroed
+    uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf
+    PairStats* stats;
+    int d, M, dsub, nprobe, k;
+};
+
+constexpr int kScanCap = 2048;
+constexpr int kScanUnroll = 4;
+constexpr int kScanTile = kThreads * kScanUnroll;
+
+template <int VEC>
+__device__ __forceinline__ float adc_one(const float* __restrict__ lut, const uint8_t* __restrict__ code, int M);
+
+template <>
+__device__ __forceinline__ float adc_one<16>(const float* __restrict__ lut, const uint8_t* __restrict__ code,
+                                             int M) {
+    float acc = 0.0f;
+    const uint4* p = reinterpret_cast<const uint4*>(code);
+    for (int m0 = 0; m0 < M; m0 += 16) {
+        uint4 v = __ldg(p + (m0 >> 4));
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                acc = __fadd_rn(acc, lut[(m0 + i * 4 + b) * 256 + ((w[i] >> (8 * b)) & 0xffu)]);
+    }
+    return acc;
+}
+
+template <>
+__device__ __forceinline__ float adc_one<8>(const float* __restrict__ lut, const uint8_t* __restrict__ code,
+                                            int M) {
+    float acc = 0.0f;
+    const uint2* p = reinterpret_cast<const uint2*>(code);
+    for (int m0 = 0; m0 < M; m0 += 8) {
+        uint2 v = __ldg(p + (m0 >> 3));
+        uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                acc = __fadd_rn(acc, lut[(m0 + i * 4 + b) * 256 + ((w[i] >> (8 * b)) & 0xffu)]);
+    }
+    return acc;
+}
+
+template <>
+__device__ __forceinline__ float adc_one<4>(const float* __restrict__ lut, const uint8_t* __restrict__ code,
+                                            int M) {
+    float acc = 0.0f;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(code);
+    for (int m0 = 0; m0 < M; m0 += 4) {
+        uint32_t w = __ldg(p + (m0 >> 2));
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc = __fadd_rn(acc, lut[(m0 + b) * 256 + ((w >> (8 * b)) & 0xffu)]);
+    }
+    return acc;
+}
+
+template <>
+__device__ __forceinline__ float adc_one<1>(const float* __restrict__ lut, const uint8_t* __restrict__ code,
+                                            int M) {
+    float acc = 0.0f;
+    for (int m = 0; m < M; m++) acc = __fadd_rn(acc, lut[m * 256 + __ldg(code + m)]);
+    return acc;
+}
+
+// shared memory: [ LUT M*256 f32 | residual d f32 | TopK ]
+__host__ __device__ inline size_t scan_smem_bytes(int M, int d, int k) {
+    size_t lut = sizeof(float) * static_cast<size_t>(M) * 256;
+    size_t res = sizeof(float) * static_cast<size_t>((d + 3) & ~3);
+    return lut + res + TopK::smem_bytes(k, kScanCap);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* lut = reinterpret_cast<float*>(smem_raw);
+    float* res = lut + p.M * 256;
+    TopK tk;
+    tk.bind(res + ((p.d + 3) & ~3), p.k, kScanCap);
+    __shared__ int s_work;
+    const int tid = threadIdx.x;
+    const int nvalid = p.stats->nvalid;
+
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(&p.stats->work_counter, 1);
+        __syncthreads();
+        const int w = s_work;
+        if (w >= nvalid) break;
+        const int pair = p.order[w];
+        const int q = pair / p.nprobe;
+        const int list = p.probe[pair];
+        const int64_t beg = p.offsets[list];
+        const int64_t n = p.offsets[list + 1] - beg;
+
+        // a2: residual
+        for (int j = tid; j < p.d; j += kThreads)
+            res[j] = __fsub_rn(p.xq[static_cast<int64_t>(q) * p.d + j], p.cent[static_cast<int64_t>(list) * p.d + j]);
+        const uint32_t ext_thr = *reinterpret_cast<volatile uint32_t*>(p.qthr + q);
+        if (tid == 0) tk.reset(ext_thr);
+        __syncthreads();
+        // a3: LUT
+        for (int idx = tid; idx < p.M * 256; idx += kThreads) {
+            const int m = idx >> 8;
+            const float* pc = p.pq + static_cast<int64_t>(idx) * p.dsub;
+            const float* r = res + m * p.dsub;
+            float acc = 0.0f;
+            for (int j = 0; j < p.dsub; j++) acc = sqdiff_acc(acc, r[j], __ldg(pc + j));
+            lut[idx] = acc;
+        }
+        __syncthreads();
+        // a4 + a5
+        const uint8_t* lcodes = p.codes + beg * p.M;
+        uint32_t thr = ext_thr;
+        for (int64_t base = 0; base < n; base += kScanTile) {
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) {
+                int64_t i = base + u * kThreads + tid;
+                uint32_t bits = 0xffffffffu;
+                if (i < n) bits = __float_as_uint(adc_one<VEC>(lut, lcodes + i * p.M, p.M));
+                tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(i)));
+            }
+            __syncthreads();
+            if (tk.pending() > kScanCap - kScanTile) tk.flush<kThreads>(ext_thr);
+            thr = tk.threshold();
+        }
+        __syncthreads();
+        tk.flush<kThreads>(ext_thr);
+        const int nb = tk.count();
+        const uint64_t* s = tk.sorted();
+        for (int i = tid; i < nb; i += kThreads) p.out_keys[static_cast<int64_t>(pair) * p.k + i] = s[i];
+        if (tid == 0) {
+            p.out_cnt[pair] = nb;
+            if (nb == p.k) atomicMin(p.qthr + q, static_cast<uint32_t>(s[p.k - 1] >> 32));
+        }
+        __syncthreads();   // smem reuse by the next pair
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4b: per-query merge of the per-probe candidate lists + id lookup (a5 final order, a6).
+// Total order (distance, probe rank, offset): within a probe the list is already (distance, offset)
+// sorted, so position j stands in for the offset.  ids: ipynb:756-771 (get_invlist).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMergeCap = 2048;
+constexpr int kMergeTile = kThreads * 4;
+
+__global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* __restrict__ pair_keys,
+                                                               const int* __restrict__ pair_cnt,
+                                                               const int32_t* __restrict__ probe,
+                                                               const int64_t* __restrict__ offsets,
+                                                               const int64_t* __restrict__ ids, int nprobe, int k,
+                                                               float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TopK tk;
+    tk.bind(smem_raw, k, kMergeCap);
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    if (tid == 0) tk.reset(kInfBits);
+    __syncthreads();
+    uint32_t thr = kInfBits;
+    const int64_t total = static_cast<int64_t>(nprobe) * k;
+    for (int64_t base = 0; base < total; base += kMergeTile) {
+#pragma unroll
+        for (int u = 0; u < kMergeTile / kThreads; u++) {
+            int64_t c = base + u * kThreads + tid;
+            uint32_t bits = 0xffffffffu;
+            if (c < total) {
+                int pr = static_cast<int>(c / k), j = static_cast<int>(c % k);
+                int64_t pair = q * nprobe + pr;
+                if (j < pair_cnt[pair]) bits = static_cast<uint32_t>(pair_keys[pair * k + j] >> 32);
+            }
+            tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
+        }
+        __syncthreads();
+        if (tk.pending() > kMergeCap - kMergeTile) tk.flush<kThreads>(kInfBits);
+        thr = tk.threshold();
+    }
+    __syncthreads();
+    tk.flush<kThreads>(kInfBits);
+    const int nb = tk.count();
+    const uint64_t* s = tk.sorted();
+    for (int i = tid; i < k; i += kThreads) {
+        float dv = FLT_MAX;
+        int64_t id = -1;
+        if (i < nb) {
+            uint32_t tag = static_cast<uint32_t>(s[i] & 0xffffffffu);
+            int pr = tag / k, j = tag % k;
+            int64_t pair = q * nprobe + pr;
+            uint32_t off = static_cast<uint32_t>(pair_keys[pair * k + j] & 0xffffffffu);
+            int64_t pos = offsets[probe[pair]] + off;
+            id = ids ? ids[pos] : pos;
+            dv = __uint_as_float(static_cast<uint32_t>(s[i] >> 32));
+        }
+        D[q * k + i] = dv;
+        I[q * k + i] = id;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: merge of per-shard results after the all-gather.  Ds/Is are (nshard, nq, k); order
+// (distance, shard, position) = concatenate + stable argsort + take k
+// (bench_multi_cpu_performance_OSDI.py:203-219).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) merge_shards_kernel(const float* __restrict__ Ds,
+                                                                const int64_t* __restrict__ Is, int nshard,
+                                                                int64_t nq, int k, float* __restrict__ D,
+                                                                int64_t* __restrict__ I) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TopK tk;
+    tk.bind(smem_raw, k, kMergeCap);
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    if (tid == 0) tk.reset(kInfBits);
+    __syncthreads();
+    uint32_t thr = kInfBits;
+    const int64_t total = static_cast<int64_t>(nshard) * k;
+    for (int64_t base = 0; base < total; base += kMergeTile) {
+#pragma unroll
+        for (int u = 0; u < kMergeTile / kThreads; u++) {
+            int64_t c = base + u * kThreads + tid;
+            uint32_t bits = 0xffffffffu;
+            if (c < total) {
+                int64_t s = c / k, j = c % k;
+                int64_t src = (s * nq + q) * k + j;
+                if (Is[src] >= 0) bits = __float_as_uint(Ds[src]);
+            }
+            tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
+        }
+        __syncthreads();
+        if (tk.pending() > kMergeCap - kMergeTile) tk.flush<kThreads>(kInfBits);
+        thr = tk.threshold();
+    }
+    __syncthreads();
+    tk.flush<kThreads>(kInfBits);
+    const int nb = tk.count();
+    const uint64_t* s = tk.sorted();
+    for (int i = tid; i < k; i += kThreads) {
+        float dv = FLT_MAX;
+        int64_t id = -1;
+        if (i < nb) {
+            uint32_t tag = static_cast<uint32_t>(s[i] & 0xffffffffu);
+            int64_t sh = tag / k, j = tag % k;
+            int64_t src = (sh * nq + q) * k + j;
+            id = Is[src];
+            dv = Ds[src];
+        }
+        D[q * k + i] = dv;
+        I[q * k + i] = id;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a9: PQ encode of residuals for index.add.  grid = (ceil(n / 256), M); each CTA stages pq[m] in
+// shared memory, each thread encodes sub-vector m of one vector: argmin_k sum_j ((x-c)_j - pq[m][k][j])^2,
+// ties -> lower k.  Same arithmetic as the LUT (the code is the argmin of the vector's own LUT row).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) encode_kernel(const float* __restrict__ x,
+                                                          const float* __restrict__ cent,
+                                                          const int64_t* __restrict__ list_no,
+                                                          const float* __restrict__ pq, int64_t n, int d, int M,
+                                                          int dsub, uint8_t* __restrict__ codes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* spq = reinterpret_cast<float*>(smem_raw);              // [256 * dsub]
+    float* sres = spq + 256 * dsub;                               // [dsub][kThreads]
+    const int tid = threadIdx.x;
+    const int m = blockIdx.y;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + tid;
+    for (int e = tid; e < 256 * dsub; e += kThreads) spq[e] = pq[static_cast<int64_t>(m) * 256 * dsub + e];
+    if (i < n) {
+        const float* xv = x + i * d + m * dsub;
+        const float* cv = cent + list_no[i] * d + m * dsub;
+        for (int j = 0; j < dsub; j++) sres[j * kThreads + tid] = __fsub_rn(xv[j], cv[j]);
+    }
+    __syncthreads();
+    if (i >= n) return;
+    float best = 0.0f;
+    int arg = -1;
+    for (int kk = 0; kk < 256; kk++) {
+        float acc = 0.0f;
+        for (int j = 0; j < dsub; j++) acc = sqdiff_acc(acc, sres[j * kThreads + tid], spq[kk * dsub + j]);
+        if (arg < 0 || acc < best) {
+            best = acc;
+            arg = kk;
+        }
+    }
+    codes[i * M + m] = static_cast<uint8_t>(arg);
+}
+
+__global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+}  // namespace b200

@@ -1,0 +1,146 @@
+// topk.cuh -- exact block-level k-selection over 64-bit keys, shared by every selection on the path:
+//   coarse select   key = (distance bits << 32) | centroid id          (ties -> lower id)
+//   scan top-k      key = (distance bits << 32) | offset in list       (ties -> earlier offset)
+//   per-query merge key = (distance bits << 32) | (probe rank * k + j) (ties -> earlier probe)
+//   shard merge     key = (distance bits << 32) | (shard * k + j)
+// Distances are sums of squares, so their fp32 bit patterns order like unsigned integers and the
+// 64-bit unsigned compare is exactly the oracle's (distance, tag) total order
+// (oracle/ivfpq_oracle.c ent_less; reference compare rule priority_queue_L1.hpp:65-75, strict <).
+//
+// Mechanism: candidates that pass the running threshold (distance <= current k-th best) are appended
+// to a shared-memory queue with one warp-aggregated atomic; the queue is folded into the sorted best
+// list only when it could overflow (bitonic sort of the queue + merge-by-rank), so the common case per
+// candidate is one compare.  Keys must be distinct (they are: the tag is unique).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+constexpr uint32_t kInfBits = 0x7f800000u;   // +inf: "no threshold yet"
+constexpr uint64_t kPadKey = ~0ull;
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ uint64_t make_key(uint32_t dist_bits, uint32_t tag) {
+    return (static_cast<uint64_t>(dist_bits) << 32) | tag;
+}
+
+struct TopK {
+    uint64_t* best;   // [2 * k] ping-pong sorted lists
+    uint64_t* queue;  // [cap]
+    int* meta;        // [0] nbest  [1] qcount  [2] cur  [3] threshold bits
+    int k;
+    int cap;
+
+    static __host__ __device__ size_t smem_bytes(int k, int cap) {
+        return sizeof(uint64_t) * (2 * static_cast<size_t>(k) + cap) + 4 * sizeof(int);
+    }
+
+    // carve out of a shared-memory region (8-byte aligned)
+    __device__ void bind(void* smem, int k_, int cap_) {
+        k = k_;
+        cap = cap_;
+        best = reinterpret_cast<uint64_t*>(smem);
+        queue = best + 2 * k_;
+        meta = reinterpret_cast<int*>(queue + cap_);
+    }
+
+    // one thread; caller syncs afterwards
+    __device__ void reset(uint32_t thr_bits) {
+        meta[0] = 0;
+        meta[1] = 0;
+        meta[2] = 0;
+        meta[3] = static_cast<int>(thr_bits);
+    }
+
+    __device__ __forceinline__ uint32_t threshold() const { return static_cast<uint32_t>(meta[3]); }
+    __device__ __forceinline__ int pending() const { return meta[1]; }
+    __device__ __forceinline__ int count() const { return meta[0]; }
+    __device__ __forceinline__ const uint64_t* sorted() const { return best + meta[2] * k; }
+
+    // whole warp calls (converged); lanes with pred append their key.  Capacity is the caller's
+    // invariant: flush() is called whenever pending() + (candidates of the next tile) > cap.
+    __device__ __forceinline__ void push(bool pred, uint64_t key) {
+        unsigned mask = __ballot_sync(0xffffffffu, pred);
+        if (mask == 0) return;
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&meta[1], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pred) queue[base + __popc(mask & lanemask_lt())] = key;
+    }
+
+    static __device__ __forceinline__ int lower_bound(const uint64_t* a, int n, uint64_t key) {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (a[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    }
+
+    // all THREADS threads call, after a __syncthreads() that made the queue writes visible.
+    // ext_thr: an externally known upper bound on the k-th best distance (kInfBits if none).
+    template <int THREADS>
+    __device__ void flush(uint32_t ext_thr) {
+        const int tid = threadIdx.x;
+        const int n = meta[1];
+        if (n == 0) return;   // uniform
+        int P = 1;
+        while (P < n) P <<= 1;
+        for (int i = n + tid; i < P; i += THREADS) queue[i] = kPadKey;
+        __syncthreads();
+        for (int size = 2; size <= P; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < (P >> 1); t += THREADS) {
+                    int lo = 2 * t - (t & (stride - 1));
+                    int hi = lo + stride;
+                    bool asc = (lo & size) == 0;
+                    uint64_t a = queue[lo], b = queue[hi];
+                    if ((a > b) == asc) {
+                        queue[lo] = b;
+                        queue[hi] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const int cur = meta[2], nb = meta[0];
+        const uint64_t* old = best + cur * k;
+        uint64_t* out = best + (cur ^ 1) * k;
+        const int nnew = n < k ? n : k;   // queue is sorted: only its first k can survive
+        for (int i = tid; i < nnew; i += THREADS) {
+            uint64_t key = queue[i];
+            int r = i + lower_bound(old, nb, key);
+            if (r < k) out[r] = key;
+        }
+        for (int t = tid; t < nb; t += THREADS) {
+            uint64_t key = old[t];
+            int r = t + lower_bound(queue, nnew, key);
+            if (r < k) out[r] = key;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nn = nb + n < k ? nb + n : k;
+            meta[0] = nn;
+            meta[1] = 0;
+            meta[2] = cur ^ 1;
+            uint32_t thr = ext_thr;
+            if (nn == k) {
+                uint32_t kth = static_cast<uint32_t>(out[k - 1] >> 32);
+                thr = kth < thr ? kth : thr;
+            }
+            meta[3] = static_cast<int>(thr);
+        }
+        __syncthreads();
+    }
+};
+
+}  // namespace b200

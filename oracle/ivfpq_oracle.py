@@ -1,0 +1,284 @@
+"""CPU oracle for the IVF-PQ search path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+bench.py may import this module.  The product package (chameleon-rag-acceleration_b200/) never does.
+
+Two implementations of the same arithmetic contract (see ivfpq_oracle.c header):
+
+* ``C`` -- ctypes binding of ``libivfpq_oracle.so`` (C, OpenMP); used for anything sizeable and as the
+  CPU baseline ("restated Faiss-CPU algorithm, not the Faiss binary").
+* ``np_*`` -- a slow numpy twin, written directly from the reference's notebook functions
+  (Chameleon/Faiss_experiments/my_faiss_extract_scripts/IVFPQ_1B_search.ipynb:7922-8028), vectorised only
+  across independent outputs so that every accumulation keeps its sequential fp32 order.  It exists to
+  cross-check the C file on small cases.
+
+Parity status: LUT arithmetic pinned by the reference's literal KAT
+(retrieval_accelerator/LUT_construction_PEs/LUT_construction_PE_D128_M32/src/host.cpp:44-109);
+end-to-end search "parity unpinned" against the Faiss binary (Faiss not installable here).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libivfpq_oracle.so")
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle (gcc, a few hundred ms).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "ivfpq_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _SO
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class _C:
+    """ctypes facade over libivfpq_oracle.so."""
+
+    def __init__(self):
+        self._lib = None
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            if not os.path.exists(_SO):
+                build()
+            lib = ctypes.CDLL(_SO)
+            lib.oracle_l2sqr.restype = ctypes.c_float
+            lib.oracle_l2sqr.argtypes = [_f32p, _f32p, ctypes.c_int]
+            lib.oracle_num_threads.restype = ctypes.c_int
+            lib.oracle_set_num_threads.argtypes = [ctypes.c_int]
+            lib.oracle_coarse.argtypes = [ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int64, _f32p, ctypes.c_int,
+                                          _i64p, _f32p]
+            lib.oracle_lut.argtypes = [ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, _f32p]
+            lib.oracle_adc.argtypes = [ctypes.c_int, _f32p, ctypes.c_int64, _u8p, _f32p]
+            lib.oracle_search_preassigned.argtypes = [ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int64, _f32p,
+                                                      ctypes.c_int, _f32p, _i64p, _u8p, _i64p, ctypes.c_int, _i64p,
+                                                      ctypes.c_int, _f32p, _i64p]
+            lib.oracle_search.argtypes = [ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int64, _f32p, ctypes.c_int,
+                                          _f32p, _i64p, _u8p, _i64p, ctypes.c_int, ctypes.c_int, _f32p, _i64p, _i64p,
+                                          _f32p]
+            lib.oracle_assign.argtypes = [ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int64, _f32p, _i64p]
+            lib.oracle_encode.argtypes = [ctypes.c_int64, ctypes.c_int, _f32p, _f32p, _i64p, ctypes.c_int, _f32p, _u8p]
+            lib.oracle_merge_shards.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, _f32p, _i64p, _f32p, _i64p]
+            self._lib = lib
+        return self._lib
+
+    def num_threads(self) -> int:
+        return int(self.lib.oracle_num_threads())
+
+    def set_num_threads(self, n: int) -> None:
+        self.lib.oracle_set_num_threads(int(n))
+
+    def l2sqr(self, a, b) -> np.float32:
+        a, b = _f32(a), _f32(b)
+        return np.float32(self.lib.oracle_l2sqr(_p(a, _f32p), _p(b, _f32p), a.shape[0]))
+
+    def coarse(self, xq, centroids, nprobe):
+        xq, centroids = _f32(xq), _f32(centroids)
+        nq, d = xq.shape
+        ids = np.empty((nq, nprobe), np.int64)
+        dis = np.empty((nq, nprobe), np.float32)
+        self.lib.oracle_coarse(nq, d, _p(xq, _f32p), centroids.shape[0], _p(centroids, _f32p), nprobe, _p(ids, _i64p),
+                               _p(dis, _f32p))
+        return dis, ids
+
+    def lut(self, q, c, pq):
+        q, c, pq = _f32(q), _f32(c), _f32(pq)
+        M = pq.shape[0]
+        T = np.empty((M, 256), np.float32)
+        self.lib.oracle_lut(q.shape[0], M, _p(q, _f32p), _p(c, _f32p), _p(pq, _f32p), _p(T, _f32p))
+        return T
+
+    def adc(self, T, codes):
+        T, codes = _f32(T), _u8(codes)
+        n, M = codes.shape
+        out = np.empty(n, np.float32)
+        self.lib.oracle_adc(M, _p(T, _f32p), n, _p(codes, _u8p), _p(out, _f32p))
+        return out
+
+    def search_preassigned(self, xq, centroids, pq, offsets, codes, ids, probe_ids, k):
+        xq, centroids, pq = _f32(xq), _f32(centroids), _f32(pq)
+        offsets, codes, ids, probe_ids = _i64(offsets), _u8(codes), _i64(ids), _i64(probe_ids)
+        nq, d = xq.shape
+        D = np.empty((nq, k), np.float32)
+        I = np.empty((nq, k), np.int64)
+        self.lib.oracle_search_preassigned(nq, d, _p(xq, _f32p), centroids.shape[0], _p(centroids, _f32p), pq.shape[0],
+                                           _p(pq, _f32p), _p(offsets, _i64p), _p(codes, _u8p), _p(ids, _i64p),
+                                           probe_ids.shape[1], _p(probe_ids, _i64p), k, _p(D, _f32p), _p(I, _i64p))
+        return D, I
+
+    def search(self, xq, centroids, pq, offsets, codes, ids, nprobe, k, return_probes=False):
+        xq, centroids, pq = _f32(xq), _f32(centroids), _f32(pq)
+        offsets, codes, ids = _i64(offsets), _u8(codes), _i64(ids)
+        nq, d = xq.shape
+        D = np.empty((nq, k), np.float32)
+        I = np.empty((nq, k), np.int64)
+        pid = np.empty((nq, nprobe), np.int64)
+        pdis = np.empty((nq, nprobe), np.float32)
+        self.lib.oracle_search(nq, d, _p(xq, _f32p), centroids.shape[0], _p(centroids, _f32p), pq.shape[0],
+                               _p(pq, _f32p), _p(offsets, _i64p), _p(codes, _u8p), _p(ids, _i64p), nprobe, k,
+                               _p(D, _f32p), _p(I, _i64p), _p(pid, _i64p), _p(pdis, _f32p))
+        if return_probes:
+            return D, I, pdis, pid
+        return D, I
+
+    def assign(self, x, centroids):
+        x, centroids = _f32(x), _f32(centroids)
+        out = np.empty(x.shape[0], np.int64)
+        self.lib.oracle_assign(x.shape[0], x.shape[1], _p(x, _f32p), centroids.shape[0], _p(centroids, _f32p),
+                               _p(out, _i64p))
+        return out
+
+    def encode(self, x, centroids, list_no, pq):
+        x, centroids, pq, list_no = _f32(x), _f32(centroids), _f32(pq), _i64(list_no)
+        M = pq.shape[0]
+        codes = np.empty((x.shape[0], M), np.uint8)
+        self.lib.oracle_encode(x.shape[0], x.shape[1], _p(x, _f32p), _p(centroids, _f32p), _p(list_no, _i64p), M,
+                               _p(pq, _f32p), _p(codes, _u8p))
+        return codes
+
+    def merge_shards(self, Ds, Is):
+        """Ds, Is: (nshard, nq, k).  bench_multi_cpu_performance_OSDI.py:203-219."""
+        Ds, Is = _f32(Ds), _i64(Is)
+        nshard, nq, k = Ds.shape
+        D = np.empty((nq, k), np.float32)
+        I = np.empty((nq, k), np.int64)
+        self.lib.oracle_merge_shards(nshard, nq, k, _p(Ds, _f32p), _p(Is, _i64p), _p(D, _f32p), _p(I, _i64p))
+        return D, I
+
+
+C = _C()
+
+
+# --------------------------------------------------------------------------------------------------
+# numpy twin (small cases only)
+# --------------------------------------------------------------------------------------------------
+
+def np_l2sqr_rows(a, B):
+    """L2^2 from vector a to every row of B; sequential fp32 accumulation over j (ipynb:7922-7927)."""
+    a, B = _f32(a), _f32(B)
+    acc = np.zeros(B.shape[0], np.float32)
+    for j in range(B.shape[1]):
+        diff = (a[j] - B[:, j]).astype(np.float32)
+        acc = (acc + (diff * diff).astype(np.float32)).astype(np.float32)
+    return acc
+
+
+def np_coarse(xq, centroids, nprobe):
+    """ipynb:7991-7999: distance to every centroid, sort (ties -> lower id), take nprobe."""
+    xq = _f32(xq)
+    ids = np.empty((xq.shape[0], nprobe), np.int64)
+    dis = np.empty((xq.shape[0], nprobe), np.float32)
+    for q in range(xq.shape[0]):
+        dd = np_l2sqr_rows(xq[q], centroids)
+        order = np.lexsort((np.arange(dd.shape[0]), dd))[:nprobe]
+        ids[q], dis[q] = order, dd[order]
+    return dis, ids
+
+
+def np_lut(q, c, pq):
+    """construct_distance_table (ipynb:7929-7946) on the residual q - c (ipynb:8006)."""
+    q, c, pq = _f32(q), _f32(c), _f32(pq)
+    M, ksub, dsub = pq.shape
+    res = (q - c).astype(np.float32)
+    T = np.zeros((M, ksub), np.float32)
+    for j in range(dsub):
+        diff = (res.reshape(M, dsub)[:, j][:, None] - pq[:, :, j]).astype(np.float32)
+        T = (T + (diff * diff).astype(np.float32)).astype(np.float32)
+    return T
+
+
+def np_adc(T, codes):
+    """estimate_distance (ipynb:7948-7960): sum over m ascending, fp32."""
+    T, codes = _f32(T), _u8(codes)
+    acc = np.zeros(codes.shape[0], np.float32)
+    for m in range(codes.shape[1]):
+        acc = (acc + T[m, codes[:, m]]).astype(np.float32)
+    return acc
+
+
+def np_search_preassigned(xq, centroids, pq, offsets, codes, ids, probe_ids, k):
+    """search_single_query (ipynb:8001-8017) with the (distance, scan order) total order."""
+    xq = _f32(xq)
+    nq = xq.shape[0]
+    D = np.full((nq, k), FLT_MAX, np.float32)
+    I = np.full((nq, k), -1, np.int64)
+    for q in range(nq):
+        dd, ii = [], []
+        for l in probe_ids[q]:
+            if l < 0:
+                continue
+            beg, end = int(offsets[l]), int(offsets[l + 1])
+            if end == beg:
+                continue
+            T = np_lut(xq[q], centroids[l], pq)
+            dd.append(np_adc(T, codes[beg:end]))
+            ii.append(ids[beg:end])
+        if not dd:
+            continue
+        dd, ii = np.concatenate(dd), np.concatenate(ii)
+        order = np.lexsort((np.arange(dd.shape[0]), dd))[:k]
+        D[q, :order.shape[0]] = dd[order]
+        I[q, :order.shape[0]] = ii[order]
+    return D, I
+
+
+def np_search(xq, centroids, pq, offsets, codes, ids, nprobe, k):
+    _, pid = np_coarse(xq, centroids, nprobe)
+    return np_search_preassigned(xq, centroids, pq, offsets, codes, ids, pid, k)
+
+
+def np_merge_shards(Ds, Is):
+    """bench_multi_cpu_performance_OSDI.py:203-219: concatenate, stable argsort, take k."""
+    nshard, nq, k = Ds.shape
+    D = np.full((nq, k), FLT_MAX, np.float32)
+    I = np.full((nq, k), -1, np.int64)
+    for q in range(nq):
+        dd, ii = Ds[:, q, :].reshape(-1), Is[:, q, :].reshape(-1)
+        keep = ii >= 0
+        dd, ii = dd[keep], ii[keep]
+        order = np.argsort(dd, kind="stable")[:k]
+        D[q, :order.shape[0]] = dd[order]
+        I[q, :order.shape[0]] = ii[order]
+    return D, I
+
+
+# --------------------------------------------------------------------------------------------------
+# recall (bench_gpu_performance_OSDI.py:196-200, 690-692)
+# --------------------------------------------------------------------------------------------------
+
+def recall_at_k(I, gt, k):
+    total = 0
+    for gt_row, row in zip(gt[:, :k], I[:, :k]):
+        total += np.intersect1d(gt_row, row).shape[0]
+    return total / float(gt[:, :k].size)
+
+
+def r1_at_k(I, gt, k):
+    return float((I[:, :k] == gt[:, :1]).sum()) / I.shape[0]
