@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py -- QPS of the IVF-PQ search hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA kernels through the C-ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
+    torchrun ... bench.py --gpus N ...                       # N ranks, index sharded by vector
+
+A "step" is one pass of the hot path (coarse -> LUT -> ADC scan -> top-k [-> all-gather -> merge]) over one
+10 000-query batch.  Default workload at N = 1 is BASELINE.json configs[1]: 100M x 128, IVF8192,PQ16x8,
+nprobe = 32, k = 10 (fits one B200: 1.6 GB codes + 0.8 GB ids).  With N > 1 the same 100M database is sharded
+by add-order position modulo N (strong scaling: fixed database and batch, value = queries / time).
+
+Everything printed besides the JSON line goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "chameleon-rag-acceleration_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CONFIGS = {
+    # name: (nb, d, nlist, M, nprobe, k, nq)   -- BASELINE.json configs
+    "c1": (1_000_000, 128, 1024, 16, 16, 10, 10_000),
+    "c2": (100_000_000, 128, 8192, 16, 32, 10, 10_000),
+    "c3": (1_000_000_000, 96, 65536, 16, 64, 100, 10_000),
+    "c4": (100_000_000, 768, 16384, 64, 32, 10, 1),
+    "c5": (100_000_000, 128, 8192, 32, 32, 10, 10_000),
+}
+METRIC = "QPS at recall@10 parity (10k-query batch) + p50 batch-1 latency, 1/2/4/8 B200"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_name(cfg, args):
+    nb, d, nlist, M, nprobe, k, nq = cfg
+    return (f"{args.config}: {nb // 1_000_000}M x {d}, IVF{nlist},PQ{M}x8, nprobe={nprobe}, k={k}, "
+            f"{nq}-query batch, synthetic clustered data")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def synth_index_cpu(cfg, seed=1234, scale_nb=None):
+    """Same-shape synthetic index built on the CPU only: random codebooks, uniformly random codes, multinomial list
+    sizes.  CPU search cost depends on the shapes (nlist, M, list sizes, nprobe, k), not on the code values."""
+    nb, d, nlist, M, nprobe, k, nq = cfg
+    if scale_nb:
+        nb = scale_nb
+    rng = np.random.default_rng(seed)
+    coarse = rng.random((nlist, d), dtype=np.float32)
+    pq = (rng.standard_normal((M, 256, d // M)) * 0.1).astype(np.float32)
+    sizes = rng.multinomial(nb, np.full(nlist, 1.0 / nlist))
+    offsets = np.zeros(nlist + 1, np.int64)
+    offsets[1:] = np.cumsum(sizes)
+    codes = rng.integers(0, 256, size=(nb, M), dtype=np.uint8)
+    ids = np.arange(nb, dtype=np.int64)
+    return coarse, pq, offsets, codes, ids
+
+
+def time_oracle(oracle, xq, arrays, nprobe, k, budget_s=15.0, max_q=None):
+    """Bounded CPU sample: pilot on 64 queries, then as many queries as fit ~budget_s.  Returns (qps, nq_used, s)."""
+    coarse, pq, offsets, codes, ids = arrays
+    npilot = min(64, xq.shape[0])
+    t0 = time.perf_counter()
+    oracle.C.search(xq[:npilot], coarse, pq, offsets, codes, ids, nprobe, k)
+    per_q = (time.perf_counter() - t0) / npilot
+    n = int(max(npilot, min(xq.shape[0] if max_q is None else max_q, budget_s / max(per_q, 1e-9))))
+    n = min(n, xq.shape[0])
+    t0 = time.perf_counter()
+    D, I = oracle.C.search(xq[:n], coarse, pq, offsets, codes, ids, nprobe, k)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt, D, I
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ivfpq_oracle as oracle
+    oracle.build()
+    cfg = CONFIGS[args.config]
+    nb, d, nlist, M, nprobe, k, nq = cfg
+    cores = oracle.C.num_threads()
+    log(f"[reference] building same-shape synthetic index on the CPU ({nb} codes) ...")
+    arrays = synth_index_cpu(cfg)
+    rng = np.random.default_rng(4321)
+    xq = rng.random((nq, d), dtype=np.float32)
+    # a step = a bounded sample of the 10k-query batch, sized from a pilot so that the run ends in minutes
+    npilot = min(32, nq)
+    t0 = time.perf_counter()
+    oracle.C.search(xq[:npilot], *arrays, nprobe, k)
+    per_q = (time.perf_counter() - t0) / npilot
+    total = args.steps + args.warmup
+    nq_step = int(max(1, min(nq, (120.0 / max(total, 1)) / max(per_q, 1e-9))))
+    log(f"[reference] {per_q * 1e3:.2f} ms/query on {cores} threads -> {nq_step} queries per step")
+    for _ in range(args.warmup):
+        oracle.C.search(xq[:nq_step], *arrays, nprobe, k)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        oracle.C.search(xq[:nq_step], *arrays, nprobe, k)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    qps = nq_step / (ms / 1e3)
+    sample = (f"{nq_step} of {nq} queries per step on a same-shape synthetic index (uniform random codes, "
+              f"multinomial list sizes); restated Faiss-CPU algorithm (oracle/ivfpq_oracle.c, OpenMP), "
+              f"not the Faiss binary")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32/u8", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, args), "queries_per_step": nq_step},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def build_index(cfg, rank, world, device, dist, args):
+    """Generate -> train -> assign/encode -> discard, chunk by chunk on the GPU.  Rank r
+    keeps add-order positions with pos % world == r.  Rank 0 also keeps exact ground truth for a query sample."""
+    import torch
+
+    import b200ivfpq as faiss
+    from b200ivfpq.datasets import SEED_BASE, SEED_QUERY, SEED_TRAIN, ClusteredGenerator
+
+    nb, d, nlist, M, nprobe, k, nq = cfg
+    gen = ClusteredGenerator(d, ncentres=max(64, min(4 * nlist, 65536)), sigma=args.sigma, device=device, seed=7)
+    index = faiss.index_factory(d, f"IVF{nlist},PQ{M}x8")
+    t0 = time.perf_counter()
+    ntrain = min(nb, max(256000, 100 * nlist))            # bench_cpu_performance.py:77-90
+    if rank == 0:
+        xt = torch.cat([gen.chunk(SEED_TRAIN, i, min(1 << 20, ntrain - i * (1 << 20)))
+                        for i in range((ntrain + (1 << 20) - 1) >> 20)])
+        index.train(xt)
+        del xt
+        coarse, pq = index.quantizer.xb_tensor(), index.pq.centroids_tensor()
+    else:
+        coarse = torch.empty((nlist, d), dtype=torch.float32, device=device)
+        pq = torch.empty((M, 256, d // M), dtype=torch.float32, device=device)
+    if world > 1:
+        dist.broadcast(coarse, 0)
+        dist.broadcast(pq, 0)
+        if rank != 0:
+            index.set_codebooks(coarse, pq)
+    torch.cuda.synchronize()
+    t_train = time.perf_counter() - t0
+
+    xq = gen.chunk(SEED_QUERY, 0, max(nq, 1))
+    ngt = min(args.gt_queries, xq.shape[0]) if rank == 0 else 0
+    gt_d = torch.full((ngt, 10), float("inf"), device=device)
+    gt_i = torch.full((ngt, 10), -1, dtype=torch.int64, device=device)
+    xq_gt = xq[:ngt]
+    qn = (xq_gt * xq_gt).sum(1, keepdim=True)
+
+    t0 = time.perf_counter()
+    chunk = 1 << 21
+    nchunks = (nb + chunk - 1) // chunk
+    for ci in range(nchunks):
+        n = min(chunk, nb - ci * chunk)
+        x = gen.chunk(SEED_BASE, ci, n)
+        pos0 = ci * chunk
+        if ngt:
+            # exact brute force for recall: ||x||^2 - 2 q.x (+ ||q||^2), fp32 library GEMM (not on the timed path)
+            dd = torch.addmm((x * x).sum(1).unsqueeze(0), xq_gt, x.t(), alpha=-2.0) + qn
+            cd, cidx = torch.topk(dd, 10, dim=1, largest=False)
+            alld = torch.cat([gt_d, cd], 1)
+            alli = torch.cat([gt_i, cidx + pos0], 1)
+            gt_d, sel = torch.topk(alld, 10, dim=1, largest=False)
+            gt_i = torch.gather(alli, 1, sel)
+            del dd
+        if world > 1:
+            first = (rank - pos0) % world
+            keep = torch.arange(first, n, world, device=device)
+            x = x[keep]
+            ids = keep + pos0
+        else:
+            ids = torch.arange(pos0, pos0 + n, device=device)
+        index.add_with_ids(x, ids)
+        del x
+        if rank == 0 and (ci % 10 == 0 or ci == nchunks - 1):
+            torch.cuda.synchronize()
+            log(f"[build] chunk {ci + 1}/{nchunks}  {time.perf_counter() - t0:.1f} s")
+    index._sync_lists()
+    torch.cuda.synchronize()
+    t_add = time.perf_counter() - t0
+    index.nprobe = nprobe
+    return index, xq[:nq].contiguous(), gt_i, {"train_s": t_train, "add_s": t_add}
+
+
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    import b200ivfpq as faiss
+    from b200ivfpq.shards import DistributedIndexIVFPQ
+
+    cfg = CONFIGS[args.config]
+    if args.nb:
+        cfg = (args.nb,) + cfg[1:]
+    if args.nq:
+        cfg = cfg[:6] + (args.nq,)
+    if args.nprobe:
+        cfg = cfg[:4] + (args.nprobe,) + cfg[5:]
+    nb, d, nlist, M, nprobe, k, nq = cfg
+    if rank == 0:
+        log(f"[bench] {workload_name(cfg, args)} on {world} GPU(s)")
+    index, xq, gt, build_info = build_index(cfg, rank, world, device, dist, args)
+    searcher = DistributedIndexIVFPQ(index) if world > 1 else index
+    index.set_stage_timing(True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return searcher.search(xq, k)
+
+    # ---- parity + recall (outside the timed region) -----------------------------------------------------
+    D, I = step_device()
+    torch.cuda.synchronize()
+    stats = index.last_scan_stats()
+    recall = None
+    if rank == 0 and gt.shape[0]:
+        ng = gt.shape[0]
+        Ic, gc = I[:ng, :10].cpu().numpy(), gt.cpu().numpy()
+        recall = float(sum(np.intersect1d(a, b).shape[0] for a, b in zip(Ic, gc)) / gc.size)
+        log(f"[bench] recall@10 on {ng} queries = {recall:.4f}; scan bytes/query = {stats['bytes'] / nq / 1e6:.2f} MB")
+
+    # ---- timed region: queries resident in HBM, results left in HBM ------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = faiss.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms, stage_acc = [], {}
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    launches = faiss.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    qps = nq / (ms_per_step / 1e3)
+
+    # per-stage device times (CUDA events recorded by the library on the launching stream); a few extra steps
+    for _ in range(min(args.steps, 5)):
+        step_device()
+        st = index.stage_ms()
+        scan_ms.append(st["scan"])
+        for kk, v in st.items():
+            stage_acc.setdefault(kk, []).append(v)
+    stages = {kk: float(np.mean(v)) for kk, v in stage_acc.items()}
+    scan_t = float(np.mean(scan_ms))
+
+    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ------------------
+    xq_host = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
+    xq_host.copy_(xq)
+    xq_np = xq_host.numpy()
+
+    def step_host():
+        if world == 1:
+            return index.search(xq_np, k)                  # b200_ivfpq_search_host: H2D, kernels, D2H, sync
+        Dd, Id = searcher.search(xq_host.to(device, non_blocking=True), k)
+        return Dd.cpu(), Id.cpu()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.item()) / args.steps
+    e2e_qps = nq / (e2e_ms / 1e3)
+
+    # ---- batch-1 latency (p50 over 200 single-query searches, host in / host out) ---------------------
+    lat = []
+    q1 = xq_np[:1].copy()
+    for i in range(220):
+        qi = xq_np[i % nq:i % nq + 1]
+        t0 = time.perf_counter()
+        if world == 1:
+            index.search(qi, k)
+        else:
+            Dd, Id = searcher.search(torch.from_numpy(qi).to(device), k)
+            Dd.cpu()
+        if i >= 20:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    lat_p50 = float(np.median(lat))
+    del q1
+
+    # ---- roofline of the dominant kernel (K2+K3+K4 scan) -----------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = stats["bytes"] / (scan_t / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("config") == args.config and tj.get("n_gpus", 1) == world:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "scan (K2+K3+K4: LUT + ADC + top-k)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": stats["bytes"], "launch_ms": scan_t,
+                "note": "algorithmic bytes = sum over probed lists of list_size*M; codes of a list are re-read "
+                        "from L2 by the ~nq*nprobe/nlist queries that probe it, so DRAM traffic << algorithmic"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle on the SAME index and queries --------------
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ivfpq_oracle as oracle
+        oracle.build()
+        a = index.to_arrays()
+        arrays = (a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"])
+        cqps, n_used, dt, Dr, Ir = time_oracle(oracle, xq_np, arrays, nprobe, k, budget_s=args.cpu_budget_s)
+        Dg, Ig = D[:n_used].cpu().numpy(), I[:n_used].cpu().numpy()
+        parity = {"queries": int(n_used),
+                  "distances_bit_exact": bool(np.array_equal(Dg.view(np.uint32), Dr.view(np.uint32))),
+                  "ids_identical": bool(np.array_equal(Ig, Ir)),
+                  "max_rel_dist_err": float(np.max(np.abs(Dg - Dr) / np.maximum(np.abs(Dr), 1e-30)))}
+        if gt.shape[0]:
+            ng = min(gt.shape[0], n_used)
+            gc = gt[:ng].cpu().numpy()
+            parity["recall_at_10_oracle"] = float(
+                sum(np.intersect1d(x_, y_).shape[0] for x_, y_ in zip(Ir[:ng, :10], gc)) / gc.size)
+            parity["recall_at_10_ours_same_queries"] = float(
+                sum(np.intersect1d(x_, y_).shape[0] for x_, y_ in zip(Ig[:ng, :10], gc)) / gc.size)
+        cpu_baseline = {"value": cqps, "unit": "queries/s", "cores": oracle.C.num_threads(), "kind": "port",
+                        "sample": f"first {n_used} of {nq} queries, same index and queries as the GPU run, "
+                                  f"{dt:.1f} s; restated Faiss-CPU algorithm (oracle, OpenMP), not the Faiss binary"}
+        log(f"[bench] cpu baseline {cqps:.1f} q/s on {cpu_baseline['cores']} threads; parity {parity}")
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32/u8", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, args), "sharding": f"by vector, position % {world}",
+                       "l2_policy": "inputs larger than L2 (codes %.0f MB per GPU vs 126 MB L2)" %
+                                    (index.ntotal * M / 1e6),
+                       "scan_kernel": os.environ.get("B200_IVFPQ_SCAN", "auto"), "ntotal_per_gpu": index.ntotal,
+                       "build": build_info},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * d * 4,
+                    "d2h_bytes_per_step": nq * k * 12},
+            "latency_batch1_ms_p50": lat_p50, "recall_at_10": recall, "stages_ms": stages,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_oracle": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--nb", type=int, default=0, help="override database size (exploration only)")
+    ap.add_argument("--nq", type=int, default=0)
+    ap.add_argument("--nprobe", type=int, default=0)
+    ap.add_argument("--sigma", type=float, default=0.08)
+    ap.add_argument("--gt-queries", type=int, default=1000)
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: timing rules ask for >= 3 warm-up steps")
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -110,7 +110,7 @@ class DistributedIndexIVFPQ:
         if self.world == 1:
             return D, I
         mine = pack_results(D, I)
-        gathered = torch.empty((self.world,) + mine.shape, dtype=mine.dtype, device=mine.device)
+        gathered = torch.empty((self.world * mine.shape[0],) + mine.shape[1:], dtype=mine.dtype, device=mine.device)
         self.dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        Ds, Is = unpack_results(gathered)
+        Ds, Is = unpack_results(gathered.view((self.world,) + mine.shape))
         return self._merge(Ds, Is)

@@ -117,8 +117,7 @@ __global__ void __launch_bounds__(kThreads) coarse_select_kernel(const float* __
             if (c < nlist) bits = __float_as_uint(row[c]);
             tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
         }
-        __syncthreads();
-        if (tk.pending() > kSelCap - kSelTile) tk.flush<kThreads>(kInfBits);
+        tk.sync_and_flush_if_over<kThreads>(kSelCap - kSelTile, kInfBits);
         thr = tk.threshold();
     }
     __syncthreads();
@@ -379,8 +378,7 @@ __global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p
                 if (i < n) bits = __float_as_uint(adc_one<VEC>(lut, lcodes + i * p.M, p.M));
                 tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(i)));
             }
-            __syncthreads();
-            if (tk.pending() > kScanCap - kScanTile) tk.flush<kThreads>(ext_thr);
+            tk.sync_and_flush_if_over<kThreads>(kScanCap - kScanTile, ext_thr);
             thr = tk.threshold();
         }
         __syncthreads();
@@ -431,8 +429,7 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
             }
             tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
         }
-        __syncthreads();
-        if (tk.pending() > kMergeCap - kMergeTile) tk.flush<kThreads>(kInfBits);
+        tk.sync_and_flush_if_over<kThreads>(kMergeCap - kMergeTile, kInfBits);
         thr = tk.threshold();
     }
     __syncthreads();
@@ -486,8 +483,7 @@ __global__ void __launch_bounds__(kThreads) merge_shards_kernel(const float* __r
             }
             tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
         }
-        __syncthreads();
-        if (tk.pending() > kMergeCap - kMergeTile) tk.flush<kThreads>(kInfBits);
+        tk.sync_and_flush_if_over<kThreads>(kMergeCap - kMergeTile, kInfBits);
         thr = tk.threshold();
     }
     __syncthreads();

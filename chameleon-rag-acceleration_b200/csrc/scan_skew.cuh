@@ -61,7 +61,7 @@ __device__ __forceinline__ uint4 skew_load_code16(const uint8_t* __restrict__ lc
 template <int B>
 __device__ __forceinline__ float skew_lookup(const char* __restrict__ lutb, uint32_t w, uint32_t loff, int p) {
     // result byte0 = loff (4*lane < 128), byte1 = byte B of w, bytes 2,3 = 0  ->  (c << 8) | 4*lane
-    uint32_t a = __byte_perm(w, loff, 0x6540 | (B << 4));
+    uint32_t a = __byte_perm(w, loff, 0x6504 | (B << 4));
     return *reinterpret_cast<const float*>(lutb + a + 4 * p);
 }
 
@@ -177,8 +177,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
                     pf1 = pf2;
                 }
             }
-            __syncthreads();
-            if (tk.pending() > kScanCap - kThreads * kSkewTB) tk.flush<kThreads>(ext_thr);
+            tk.sync_and_flush_if_over<kThreads>(kScanCap - kThreads * kSkewTB, ext_thr);
             thr = tk.threshold();
         }
         __syncthreads();

@@ -76,6 +76,16 @@ struct TopK {
         if (pred) queue[base + __popc(mask & lanemask_lt())] = key;
     }
 
+    // Barrier + uniform flush decision in one step.  Every thread evaluates "pending > limit" after its own
+    // pushes and the barrier ORs the votes: the last thread to vote sees every push, so all threads get the
+    // same answer (a plain read after a __syncthreads() would race with fast threads already pushing the
+    // next tile).  Returns after the queue has room for another tile.
+    template <int THREADS>
+    __device__ __forceinline__ void sync_and_flush_if_over(int limit, uint32_t ext_thr) {
+        const int seen = *reinterpret_cast<volatile int*>(&meta[1]);
+        if (__syncthreads_or(seen > limit)) flush<THREADS>(ext_thr);
+    }
+
     static __device__ __forceinline__ int lower_bound(const uint64_t* a, int n, uint64_t key) {
         int lo = 0, hi = n;
         while (lo < hi) {

@@ -1,0 +1,79 @@
+"""The N > 1 path on CPU: world_size 2 over gloo.  The exchange logic of DistributedIndexIVFPQ (pack, one
+all-gather, unpack, merge) runs for real; the per-shard search and the merge kernel -- CUDA on the product
+path -- are replaced by the oracle through the injection points, which is the only way to exercise the
+collective plumbing without a GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import _util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "chameleon-rag-acceleration_b200"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    from oracle import ivfpq_oracle as oracle
+    from b200ivfpq.shards import DistributedIndexIVFPQ
+    import _util as U
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a = U.make_index_arrays(oracle, 17, 32, 16, 8, 3000, id_scramble=False)
+        xq = U.make_queries(6, a, 24)
+        nprobe, k = 5, 10
+        sizes = np.diff(a["offsets"])
+        list_no = np.repeat(np.arange(16), sizes)
+        keep = (a["ids"] % world) == rank                     # shard by add-order position
+        off = np.zeros(17, np.int64)
+        off[1:] = np.cumsum(np.bincount(list_no[keep], minlength=16))
+        codes, ids = a["codes"][keep], a["ids"][keep]
+
+        def local_search(x, kk):
+            D, I = oracle.C.search(x.numpy(), a["coarse"], a["pq"], off, codes, ids, nprobe, kk)
+            return torch.from_numpy(D), torch.from_numpy(I)
+
+        def merge(Ds, Is):
+            D, I = oracle.C.merge_shards(Ds.numpy(), Is.numpy())
+            return torch.from_numpy(D), torch.from_numpy(I)
+
+        class _Local:
+            nprobe = 5
+            d = 32
+
+        index = DistributedIndexIVFPQ(_Local(), merge_fn=merge, local_search_fn=local_search)
+        assert index.world == world and index.rank == rank
+        D, I = index.search(torch.from_numpy(xq), k)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), D=D.numpy(), I=I.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world2_gloo_exchange_and_merge(oracle, tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a = _util.make_index_arrays(oracle, 17, 32, 16, 8, 3000, id_scramble=False)
+    xq = _util.make_queries(6, a, 24)
+    D, I = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 5, 10)
+    outs = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    _util.assert_bit_equal(outs[0]["D"], outs[1]["D"], "ranks agree on D")
+    _util.assert_bit_equal(outs[0]["I"], outs[1]["I"], "ranks agree on I")
+    _util.assert_same_modulo_ties(outs[0]["D"], outs[0]["I"], D, I, "sharded vs single index")

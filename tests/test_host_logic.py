@@ -1,0 +1,138 @@
+"""Host-side logic that needs no GPU: factory grammar, ParameterSpace, shard arithmetic, the C-ABI exports,
+and that the product path fails loudly (never falls back) without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import _util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    import b200ivfpq
+    header = open(os.path.join(ROOT, "include", "b200_ivfpq.h")).read()
+    declared = re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_ivfpq_\w+)\s*\(", header)
+    assert len(declared) >= 16
+    lib = ctypes.CDLL(b200ivfpq.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200_ivfpq.h but not exported"
+    from b200ivfpq._lib import SYMBOLS
+    assert sorted(declared) == sorted(s[0] for s in SYMBOLS), "ctypes table out of sync with the header"
+    assert b"sm_100a" in b200ivfpq.load_library().b200_ivfpq_version()
+
+
+def test_cabi_argument_errors_without_gpu():
+    """Pure argument validation happens before any CUDA call."""
+    import b200ivfpq
+    lib = b200ivfpq.load_library()
+    h = ctypes.c_void_p()
+    assert lib.b200_ivfpq_create(128, 16, 16, 4, ctypes.byref(h)) == 5          # nbits != 8 -> EUNSUPPORTED
+    assert b"nbits" in lib.b200_ivfpq_last_error()
+    assert lib.b200_ivfpq_create(100, 16, 16, 8, ctypes.byref(h)) == 1          # d % m != 0 -> EINVAL
+    assert lib.b200_ivfpq_create(0, 16, 16, 8, ctypes.byref(h)) == 1
+    assert lib.b200_ivfpq_merge_shards(0, 1, 1, None, None, None, None, None) == 1
+    assert lib.b200_ivfpq_launch_count() >= 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import b200ivfpq as faiss
+    lib = faiss.load_library()
+    h = ctypes.c_void_p()
+    rc = lib.b200_ivfpq_create(128, 16, 16, 8, ctypes.byref(h))
+    assert rc == 3 and b"no CPU path" in lib.b200_ivfpq_last_error()
+    index = faiss.index_factory(32, "IVF4,PQ4")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        index.train(np.zeros((100, 32), np.float32))
+    with pytest.raises(RuntimeError):
+        faiss.IndexFlatL2(8).add(np.zeros((4, 8), np.float32))
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing in the product package may import, link, load or execute it
+    (comments that cite the contract are fine)."""
+    pkg = os.path.join(ROOT, "chameleon-rag-acceleration_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dp, f)
+            if f.endswith(".py"):
+                text = open(path).read()
+                for pat in ("import oracle", "from oracle", "ivfpq_oracle", "libivfpq_oracle"):
+                    assert pat not in text, (path, pat)
+            elif f.endswith((".cu", ".cuh", ".h", ".sh")):
+                for line in open(path):
+                    if "oracle" in line.lower():
+                        code = line.split("//")[0]
+                        assert "oracle" not in code.lower(), (path, line)
+                        assert "#include" not in line and "dlopen" not in line, (path, line)
+
+
+def test_index_factory_grammar():
+    import b200ivfpq as faiss
+    for key, nlist, m in [("IVF1024,PQ16", 1024, 16), ("IVF8192,PQ16x8", 8192, 16), ("IVF65536,PQ16x8", 65536, 16),
+                          ("IVF16384,PQ64x8", 16384, 64), ("IVF8192,PQ32x8", 8192, 32)]:
+        d = 768 if m == 64 else 128
+        idx = faiss.index_factory(d, key)
+        assert isinstance(idx, faiss.IndexIVFPQ)
+        assert (idx.nlist, idx.pq.M, idx.pq.nbits, idx.d, idx.nprobe, idx.ntotal) == (nlist, m, 8, d, 1, 0)
+        assert idx.pq.dsub == d // m and idx.pq.ksub == 256 and idx.pq.code_size == m
+        assert not idx.is_trained
+    assert isinstance(faiss.index_factory(64, "Flat"), faiss.IndexFlatL2)
+    for bad in ["IVF1024,PQ16x4", "OPQ16,IVF1024,PQ16", "IVF1024,Flat", "IMI2x8,PQ16", "IVF,PQ16", "garbage"]:
+        with pytest.raises(RuntimeError):
+            faiss.index_factory(128, bad)
+    with pytest.raises(RuntimeError):
+        faiss.index_factory(100, "IVF16,PQ16")    # d % M
+
+
+def test_parameter_space():
+    import b200ivfpq as faiss
+    idx = faiss.index_factory(128, "IVF1024,PQ16")
+    ps = faiss.ParameterSpace()
+    ps.initialize(idx)
+    ps.set_index_parameters(idx, "nprobe=32")        # bench_cpu_performance.py:252
+    assert idx.nprobe == 32
+    ps.set_index_parameter(idx, "nprobe", 4.0)
+    assert idx.nprobe == 4
+    with pytest.raises(RuntimeError):
+        ps.set_index_parameters(idx, "ht=64")
+    with pytest.raises(RuntimeError):
+        ps.set_index_parameters(idx, "nprobe")
+    idx.parallel_mode = 3                             # faiss_retriever.py:71, accepted and ignored
+    faiss.omp_set_num_threads(4)
+
+
+def test_shard_positions_partition():
+    from b200ivfpq.shards import shard_positions
+    for n, world in [(10, 3), (1, 4), (0, 2), (1000, 8)]:
+        parts = [shard_positions(n, r, world) for r in range(world)]
+        allp = np.sort(np.concatenate(parts))
+        assert np.array_equal(allp, np.arange(n))
+        assert all((p % world == r).all() for r, p in enumerate(parts))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_pack_unpack_roundtrip_cpu():
+    from b200ivfpq.shards import pack_results, unpack_results
+    g = torch.Generator().manual_seed(0)
+    D = torch.rand((5, 7), generator=g)
+    I = torch.randint(-1, 2 ** 40, (5, 7), generator=g, dtype=torch.int64)
+    buf = pack_results(D, I)
+    assert buf.dtype == torch.int32 and buf.shape == (5, 7, 3)
+    D2, I2 = unpack_results(buf)
+    assert torch.equal(D2, D) and torch.equal(I2, I)
+
+
+def test_uniform_reference_generator_matches_the_script():
+    """datasets.uniform_reference restates IVFPQ_random_dataset.py:6-13."""
+    from b200ivfpq.datasets import uniform_reference
+    xb, xq = uniform_reference(1000, 10, 16)
+    np.random.seed(1234)
+    ref = np.random.random((1000, 16)).astype("float32")
+    ref[:, 0] += np.arange(1000) / 1000.
+    assert np.array_equal(xb, ref) and xq.shape == (10, 16) and xq.dtype == np.float32
