@@ -195,7 +195,8 @@ def build_index(cfg, rank, world, device, dist, args):
     from b200ivfpq.datasets import SEED_BASE, SEED_QUERY, SEED_TRAIN, ClusteredGenerator
 
     nb, d, nlist, M, nprobe, k, nq = cfg
-    gen = ClusteredGenerator(d, ncentres=max(64, min(4 * nlist, 65536)), sigma=args.sigma, device=device, seed=7)
+    gen = ClusteredGenerator(d, ncentres=args.ncentres or max(64, min(4 * nlist, 65536)), sigma=args.sigma,
+                             device=device, seed=7, latent_dim=args.latent_dim, sigma_iso=args.sigma_iso)
     index = faiss.index_factory(d, f"IVF{nlist},PQ{M}x8")
     t0 = time.perf_counter()
     ntrain = min(nb, max(256000, 100 * nlist))            # bench_cpu_performance.py:77-90
@@ -465,6 +466,9 @@ def main():
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--nprobe", type=int, default=0)
     ap.add_argument("--sigma", type=float, default=0.08)
+    ap.add_argument("--sigma-iso", type=float, default=0.004)
+    ap.add_argument("--latent-dim", type=int, default=12)
+    ap.add_argument("--ncentres", type=int, default=0)
     ap.add_argument("--gt-queries", type=int, default=1000)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

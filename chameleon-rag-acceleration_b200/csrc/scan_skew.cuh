@@ -52,9 +52,9 @@ __global__ void pq_transpose_kernel(const float* __restrict__ pq, float* __restr
     pq_t[(static_cast<int64_t>(c) * dsub + j) * M + m] = pq[i];
 }
 
-__device__ __forceinline__ uint4 skew_load_code16(const uint8_t* __restrict__ lcodes, int64_t idx, int64_t n) {
+__device__ __forceinline__ uint4 skew_load_code16(const uint4* __restrict__ lp, uint32_t idx, uint32_t n) {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (idx < n) v = __ldg(reinterpret_cast<const uint4*>(lcodes) + idx);
+    if (idx < n) v = __ldg(lp + idx);
     return v;
 }
 
@@ -65,6 +65,35 @@ __device__ __forceinline__ float skew_lookup(const char* __restrict__ lutb, uint
     return *reinterpret_cast<const float*>(lutb + a + 4 * p);
 }
 
+// One block = 16 lookups per lane over the byte window [r, r+16) of cur|nxt.  acc carries the partial sum of the
+// code the lane is on; the return value is the finished distance of the code that completed in this block.
+__device__ __forceinline__ float skew_block16(const char* __restrict__ lutb, const uint4& cur, const uint4& nxt,
+                                              bool ws2, bool ws1, uint32_t bs, uint32_t loff,
+                                              const float (&keep)[16], const float (&cap)[16], float& acc) {
+    // window = bytes [r, r+16) of cur|nxt: word shift by r/4 (two select stages), then a funnel shift by 8*(r%4)
+    const uint32_t y0 = ws2 ? cur.z : cur.x, y1 = ws2 ? cur.w : cur.y, y2 = ws2 ? nxt.x : cur.z,
+                   y3 = ws2 ? nxt.y : cur.w, y4 = ws2 ? nxt.z : nxt.x, y5 = ws2 ? nxt.w : nxt.y;
+    const uint32_t z0 = ws1 ? y1 : y0, z1 = ws1 ? y2 : y1, z2 = ws1 ? y3 : y2, z3 = ws1 ? y4 : y3,
+                   z4 = ws1 ? y5 : y4;
+    const uint32_t w0 = __funnelshift_r(z0, z1, bs), w1 = __funnelshift_r(z1, z2, bs),
+                   w2 = __funnelshift_r(z2, z3, bs), w3 = __funnelshift_r(z3, z4, bs);
+    float fin = 0.0f;
+#define SKEW_STEP(W, B, P)                              \
+    {                                                   \
+        float T = skew_lookup<B>(lutb, W, loff, P);     \
+        acc = __fmaf_rn(acc, keep[P], T);               \
+        fin = __fmaf_rn(acc, cap[P], fin);              \
+    }
+    SKEW_STEP(w0, 0, 0) SKEW_STEP(w0, 1, 1) SKEW_STEP(w0, 2, 2) SKEW_STEP(w0, 3, 3)
+    SKEW_STEP(w1, 0, 4) SKEW_STEP(w1, 1, 5) SKEW_STEP(w1, 2, 6) SKEW_STEP(w1, 3, 7)
+    SKEW_STEP(w2, 0, 8) SKEW_STEP(w2, 1, 9) SKEW_STEP(w2, 2, 10) SKEW_STEP(w2, 3, 11)
+    SKEW_STEP(w3, 0, 12) SKEW_STEP(w3, 1, 13) SKEW_STEP(w3, 2, 14) SKEW_STEP(w3, 3, 15)
+#undef SKEW_STEP
+    return fin;
+}
+
+// DSUB = d / 16 when it is one of the specialised values (residual slice held in registers), 0 = generic.
+template <int DSUB>
 __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanParams p, const float* __restrict__ pq_t) {
     constexpr int M = 16;
     extern __shared__ __align__(1024) unsigned char smem_skew[];
@@ -75,8 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
     int* s_work = tk.meta + 4;
     const char* lutb = reinterpret_cast<const char*>(lut);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kWarps = kThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int r = lane & (M - 1);
     const int pstart = (M - r) & (M - 1);   // step at which this lane starts a new code (m == 0)
     const int pend = M - 1 - r;             // step at which this lane finishes a code (m == 15)
@@ -90,6 +118,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
     const bool ws2 = (r & 8) != 0, ws1 = (r & 4) != 0;
     const uint32_t bs = static_cast<uint32_t>(r & 3) * 8u;
     const int nvalid = p.stats->nvalid;
+    const int dsub = DSUB ? DSUB : p.dsub;
+    // LUT build mapping: this thread owns sub-quantizer lm and code values lc0 + 16 i; the two half-warps store
+    // their 4 periodic copies in opposite order so that the 32 lanes always hit 32 distinct banks
+    const int lm = tid & (M - 1), lc0 = tid >> 4;
+    const int copy0 = (lane >> 4) * 16;
 
     for (;;) {
         if (tid == 0) *s_work = atomicAdd(&p.stats->work_counter, 1);
@@ -100,19 +133,15 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         const int q = pair / p.nprobe;
         const int list = p.probe[pair];
         const int64_t beg = p.offsets[list];
-        const int64_t n = p.offsets[list + 1] - beg;
-        const uint8_t* lcodes = p.codes + beg * M;
+        const uint32_t n = static_cast<uint32_t>(p.offsets[list + 1] - beg);
+        const uint4* lp = reinterpret_cast<const uint4*>(p.codes + beg * M);
 
-        // issue the first code loads before building the LUT so that they overlap it
-        const int64_t nblocks = (n + 31) >> 5;
-        const int Bw = nblocks > warp ? static_cast<int>((nblocks - warp + kWarps - 1) / kWarps) : 0;
-        const int maxBw = static_cast<int>((nblocks + kWarps - 1) / kWarps);
-        auto code_index = [&](int b) -> int64_t {   // global code index of this lane in its b-th block
-            return (static_cast<int64_t>(b) * kWarps + warp) * 32 + lane;
-        };
-        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
-        uint4 nxt = skew_load_code16(lcodes, 0 < Bw ? code_index(0) : n, n);
-        uint4 pf1 = skew_load_code16(lcodes, 1 < Bw ? code_index(1) : n, n);
+        // lane's code in block b is b*256 + tid.  Ring of four code registers: slot (b+1)%4 holds code b.
+        // Issue the first loads before building the LUT so that they overlap it.
+        uint4 c0 = make_uint4(0u, 0u, 0u, 0u);                    // "code -1" of the prologue block
+        uint4 c1 = skew_load_code16(lp, tid, n);                  // code 0
+        uint4 c2 = skew_load_code16(lp, 256u + tid, n);           // code 1
+        uint4 c3;
 
         // a2: residual
         for (int j = tid; j < p.d; j += kThreads)
@@ -120,63 +149,63 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         const uint32_t ext_thr = *reinterpret_cast<volatile uint32_t*>(p.qthr + q);
         if (tid == 0) tk.reset(ext_thr);
         __syncthreads();
-        // a3: LUT, periodic rows.  idx -> (c = idx / 16, m = idx % 16): a warp writes 16 distinct banks
-        // twice; pq_t is read with m fastest.
-        for (int idx = tid; idx < M * 256; idx += kThreads) {
-            const int m = idx & (M - 1), c = idx >> 4;
-            const float* pc = pq_t + static_cast<int64_t>(c) * p.dsub * M + m;
-            const float* rr = res + m * p.dsub;
-            float acc = 0.0f;
-            for (int j = 0; j < p.dsub; j++) acc = sqdiff_acc(acc, rr[j], __ldg(pc + j * M));
-            float* row = lut + c * kSkewRowWords + m;
-            row[0] = acc;
-            row[16] = acc;
-            row[32] = acc;
+        // a3: LUT with periodic rows lut[c][w] = T[w % 16][c], w < 64
+        if (DSUB) {
+            float rr[DSUB ? DSUB : 1];
+#pragma unroll
+            for (int j = 0; j < (DSUB ? DSUB : 1); j++) rr[j] = res[lm * DSUB + j];
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int c = lc0 + 16 * i;
+                const float* pc = pq_t + static_cast<int64_t>(c) * (DSUB * M) + lm;
+                float pv[DSUB ? DSUB : 1];
+#pragma unroll
+                for (int j = 0; j < (DSUB ? DSUB : 1); j++) pv[j] = __ldg(pc + j * M);
+                float a = 0.0f;
+#pragma unroll
+                for (int j = 0; j < (DSUB ? DSUB : 1); j++) a = sqdiff_acc(a, rr[j], pv[j]);
+                float* row = lut + c * kSkewRowWords + lm;
+                row[copy0] = a;
+                row[copy0 ^ 16] = a;
+                row[32 + copy0] = a;
+                row[32 + (copy0 ^ 16)] = a;
+            }
+        } else {
+            for (int i = 0; i < 16; i++) {
+                const int c = lc0 + 16 * i;
+                const float* pc = pq_t + static_cast<int64_t>(c) * dsub * M + lm;
+                const float* rr = res + lm * dsub;
+                float a = 0.0f;
+                for (int j = 0; j < dsub; j++) a = sqdiff_acc(a, rr[j], __ldg(pc + j * M));
+                float* row = lut + c * kSkewRowWords + lm;
+                row[copy0] = a;
+                row[copy0 ^ 16] = a;
+                row[32 + copy0] = a;
+                row[32 + (copy0 ^ 16)] = a;
+            }
         }
         __syncthreads();
 
-        // a4 + a5
+        // a4 + a5.  Iteration `it` processes block b = it - 1 (it = 0 is the prologue that only feeds bytes
+        // 0..r-1 of code 0).  Four iterations per tile, fully unrolled so that the code ring needs no moves.
         uint32_t thr = ext_thr;
         float acc = 0.0f;
-        const int niter = maxBw + 1;   // +1: prologue block that only feeds bytes 0..r-1 of code 0
-        for (int t0 = 0; t0 < niter; t0 += kSkewTB) {
-#pragma unroll 1
-            for (int tb = 0; tb < kSkewTB; tb++) {
-                const int b = t0 + tb - 1;
-                if (b < Bw) {
-                    uint4 pf2 = skew_load_code16(lcodes, b + 3 < Bw ? code_index(b + 3) : n, n);
-                    // window = bytes [r, r+16) of cur|nxt: word shift by r/4 (two select stages), then a
-                    // funnel shift by 8*(r%4)
-                    uint32_t x0 = cur.x, x1 = cur.y, x2 = cur.z, x3 = cur.w, x4 = nxt.x, x5 = nxt.y, x6 = nxt.z,
-                             x7 = nxt.w;
-                    uint32_t y0 = ws2 ? x2 : x0, y1 = ws2 ? x3 : x1, y2 = ws2 ? x4 : x2, y3 = ws2 ? x5 : x3,
-                             y4 = ws2 ? x6 : x4, y5 = ws2 ? x7 : x5;
-                    uint32_t z0 = ws1 ? y1 : y0, z1 = ws1 ? y2 : y1, z2 = ws1 ? y3 : y2, z3 = ws1 ? y4 : y3,
-                             z4 = ws1 ? y5 : y4;
-                    const uint32_t w0 = __funnelshift_r(z0, z1, bs), w1 = __funnelshift_r(z1, z2, bs),
-                                   w2 = __funnelshift_r(z2, z3, bs), w3 = __funnelshift_r(z3, z4, bs);
-                    float fin = 0.0f;
-#define SKEW_STEP(W, B, P)                                             \
-    {                                                                  \
-        float T = skew_lookup<B>(lutb, W, loff, P);                    \
-        acc = __fmaf_rn(acc, keep[P], T);                              \
-        fin = __fmaf_rn(acc, cap[P], fin);                             \
+        const uint32_t nblk = (n + 255u) >> 8;
+        for (uint32_t t0 = 0; t0 <= nblk; t0 += 4) {
+            const uint32_t base = t0 * 256u + tid;      // code index of block b = t0 (iteration t0 + 1)
+#define SKEW_ITER(CUR, NXT, LOADTO, TB)                                                         \
+    {                                                                                           \
+        LOADTO = skew_load_code16(lp, base + (TB + 2) * 256u, n);                               \
+        const float fin = skew_block16(lutb, CUR, NXT, ws2, ws1, bs, loff, keep, cap, acc);     \
+        const uint32_t idx = base + TB * 256u - 256u; /* wraps past 2^32 for the prologue block */ \
+        const uint32_t bits = __float_as_uint(fin);                                             \
+        tk.push(idx < n && bits <= thr, make_key(bits, idx));                                   \
     }
-                    SKEW_STEP(w0, 0, 0) SKEW_STEP(w0, 1, 1) SKEW_STEP(w0, 2, 2) SKEW_STEP(w0, 3, 3)
-                    SKEW_STEP(w1, 0, 4) SKEW_STEP(w1, 1, 5) SKEW_STEP(w1, 2, 6) SKEW_STEP(w1, 3, 7)
-                    SKEW_STEP(w2, 0, 8) SKEW_STEP(w2, 1, 9) SKEW_STEP(w2, 2, 10) SKEW_STEP(w2, 3, 11)
-                    SKEW_STEP(w3, 0, 12) SKEW_STEP(w3, 1, 13) SKEW_STEP(w3, 2, 14) SKEW_STEP(w3, 3, 15)
-#undef SKEW_STEP
-                    if (b >= 0) {
-                        const int64_t idx = code_index(b);
-                        const uint32_t bits = __float_as_uint(fin);
-                        tk.push(idx < n && bits <= thr, make_key(bits, static_cast<uint32_t>(idx)));
-                    }
-                    cur = nxt;
-                    nxt = pf1;
-                    pf1 = pf2;
-                }
-            }
+            SKEW_ITER(c0, c1, c3, 0)
+            SKEW_ITER(c1, c2, c0, 1)
+            SKEW_ITER(c2, c3, c1, 2)
+            SKEW_ITER(c3, c0, c2, 3)
+#undef SKEW_ITER
             tk.sync_and_flush_if_over<kThreads>(kScanCap - kThreads * kSkewTB, ext_thr);
             thr = tk.threshold();
         }
@@ -193,19 +222,29 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
     }
 }
 
-// returns 0, or -1 on a launch error (caller reads cudaGetLastError)
-inline int launch_scan_skew(const ScanParams& sp, const float* pq_t, int64_t npairs, int num_sms, cudaStream_t st) {
+template <int DSUB>
+int launch_scan_skew_t(const ScanParams& sp, const float* pq_t, int64_t npairs, int num_sms, cudaStream_t st) {
     size_t smem = skew_smem_bytes(sp.d, sp.k);
-    if (cudaFuncSetAttribute(scan_skew16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return -1;
+    auto kernel = scan_skew16_kernel<DSUB>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_skew16_kernel, kThreads, smem) != cudaSuccess)
-        return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess) return -1;
     if (per_sm < 1) return -1;
     int64_t grid = static_cast<int64_t>(per_sm) * num_sms;
     if (grid > npairs) grid = npairs;
-    scan_skew16_kernel<<<(unsigned)grid, kThreads, smem, st>>>(sp, pq_t);
+    kernel<<<(unsigned)grid, kThreads, smem, st>>>(sp, pq_t);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+// returns 0, or -1 on a launch error (caller reads cudaGetLastError)
+inline int launch_scan_skew(const ScanParams& sp, const float* pq_t, int64_t npairs, int num_sms, cudaStream_t st) {
+    switch (sp.dsub) {
+        case 4: return launch_scan_skew_t<4>(sp, pq_t, npairs, num_sms, st);
+        case 6: return launch_scan_skew_t<6>(sp, pq_t, npairs, num_sms, st);
+        case 8: return launch_scan_skew_t<8>(sp, pq_t, npairs, num_sms, st);
+        case 16: return launch_scan_skew_t<16>(sp, pq_t, npairs, num_sms, st);
+        default: return launch_scan_skew_t<0>(sp, pq_t, npairs, num_sms, st);
+    }
 }
 
 }  // namespace b200
