@@ -30,7 +30,7 @@ namespace b200 {
 constexpr int kSkewRowWords = 64;
 constexpr int kSkewLutBytes = 256 * kSkewRowWords * 4;   // 64 KB
 constexpr int kSkewTB = 4;                                // blocks (of 32 codes) per warp per tile
-static_assert(kThreads * kSkewTB <= kScanCap / 2, "tile must fit the candidate queue twice");
+constexpr int kSkewCap = 2 * kThreads * kSkewTB;          // candidate queue: two tiles
 
 inline bool skew_supported(int M, int d, int k) {
     (void)d;
@@ -38,7 +38,7 @@ inline bool skew_supported(int M, int d, int k) {
 }
 
 __host__ __device__ inline size_t skew_smem_bytes(int d, int k) {
-    return kSkewLutBytes + sizeof(float) * static_cast<size_t>((d + 3) & ~3) + TopK::smem_bytes(k, kScanCap) + 16;
+    return kSkewLutBytes + sizeof(float) * static_cast<size_t>((d + 3) & ~3) + TopK::smem_bytes(k, kSkewCap) + 16;
 }
 
 // pq (M, 256, dsub) -> pq_t (256, dsub, M): the LUT build reads it with m fastest (coalesced).
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
     float* lut = reinterpret_cast<float*>(smem_skew);
     float* res = lut + 256 * kSkewRowWords;
     TopK tk;
-    tk.bind(res + ((p.d + 3) & ~3), p.k, kScanCap);
+    tk.bind(res + ((p.d + 3) & ~3), p.k, kSkewCap);
     int* s_work = tk.meta + 4;
     const char* lutb = reinterpret_cast<const char*>(lut);
 
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         uint32_t thr = ext_thr;
         float acc = 0.0f;
         const uint32_t nblk = (n + 255u) >> 8;
-        for (uint32_t t0 = 0; t0 <= nblk; t0 += 4) {
-            const uint32_t base = t0 * 256u + tid;      // code index of block b = t0 (iteration t0 + 1)
+        for (uint32_t t0 = 0; t0 <= nblk; t0 += kSkewTB) {
+            uint32_t base = t0 * 256u + tid;            // code index of block b = t0 (iteration t0 + 1)
 #define SKEW_ITER(CUR, NXT, LOADTO, TB)                                                         \
     {                                                                                           \
         LOADTO = skew_load_code16(lp, base + (TB + 2) * 256u, n);                               \
@@ -201,12 +201,17 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         const uint32_t bits = __float_as_uint(fin);                                             \
         tk.push(idx < n && bits <= thr, make_key(bits, idx));                                   \
     }
-            SKEW_ITER(c0, c1, c3, 0)
-            SKEW_ITER(c1, c2, c0, 1)
-            SKEW_ITER(c2, c3, c1, 2)
-            SKEW_ITER(c3, c0, c2, 3)
+#pragma unroll
+            for (int half = 0; half < kSkewTB / 4; half++) {
+                SKEW_ITER(c0, c1, c3, 0)
+                SKEW_ITER(c1, c2, c0, 1)
+                SKEW_ITER(c2, c3, c1, 2)
+                SKEW_ITER(c3, c0, c2, 3)
+                base += 1024u;
+            }
 #undef SKEW_ITER
-            tk.sync_and_flush_if_over<kThreads>(kScanCap - kThreads * kSkewTB, ext_thr);
+            // no threshold yet (cold start): fold the first tile in right away so that later tiles are filtered
+            tk.sync_and_flush_if_over<kThreads>(thr == kInfBits ? 0 : kSkewCap - kThreads * kSkewTB, ext_thr);
             thr = tk.threshold();
         }
         __syncthreads();
