@@ -195,7 +195,7 @@ def build_index(cfg, rank, world, device, dist, args):
     from b200ivfpq.datasets import SEED_BASE, SEED_QUERY, SEED_TRAIN, ClusteredGenerator
 
     nb, d, nlist, M, nprobe, k, nq = cfg
-    gen = ClusteredGenerator(d, ncentres=args.ncentres or max(64, min(4 * nlist, 65536)), sigma=args.sigma,
+    gen = ClusteredGenerator(d, ncentres=args.ncentres or max(16, nlist // 2), sigma=args.sigma,
                              device=device, seed=7, latent_dim=args.latent_dim, sigma_iso=args.sigma_iso)
     index = faiss.index_factory(d, f"IVF{nlist},PQ{M}x8")
     t0 = time.perf_counter()
@@ -465,8 +465,8 @@ def main():
     ap.add_argument("--nb", type=int, default=0, help="override database size (exploration only)")
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--nprobe", type=int, default=0)
-    ap.add_argument("--sigma", type=float, default=0.08)
-    ap.add_argument("--sigma-iso", type=float, default=0.004)
+    ap.add_argument("--sigma", type=float, default=0.1)
+    ap.add_argument("--sigma-iso", type=float, default=0.002)
     ap.add_argument("--latent-dim", type=int, default=12)
     ap.add_argument("--ncentres", type=int, default=0)
     ap.add_argument("--gt-queries", type=int, default=1000)

@@ -32,8 +32,8 @@ class ClusteredGenerator:
     isotropic 128-d noise makes all cluster members equidistant and PQ recall collapses.
     Chunk i of a stream is generated from seed (stream_seed, i), so any rank can produce any chunk independently."""
 
-    def __init__(self, d: int, ncentres: int, sigma: float = 0.08, device="cuda", seed: int = 7, latent_dim: int = 12,
-                 sigma_iso: float = 0.004):
+    def __init__(self, d: int, ncentres: int, sigma: float = 0.1, device="cuda", seed: int = 7, latent_dim: int = 12,
+                 sigma_iso: float = 0.002):
         self.d, self.ncentres, self.sigma, self.device = d, ncentres, sigma, device
         self.latent_dim, self.sigma_iso = latent_dim, sigma_iso
         g = torch.Generator(device=device)
