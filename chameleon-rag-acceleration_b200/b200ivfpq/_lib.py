@@ -25,6 +25,8 @@ SYMBOLS = [
     ("b200_ivfpq_set_codebooks", _I, [_P, _P, _P]),
     ("b200_ivfpq_set_lists", _I, [_P, _P, _P, _P, _L]),
     ("b200_ivfpq_coarse", _I, [_P, _L, _P, _I, _P, _P, _P]),
+    ("b200_ivfpq_coarse_scores", _I, [_P, _L, _P, _P, _P]),
+    ("b200_ivfpq_coarse_fallbacks", _I, [_P, ctypes.POINTER(_L)]),
     ("b200_ivfpq_search", _I, [_P, _L, _P, _I, _I, _P, _P, _P]),
     ("b200_ivfpq_search_preassigned", _I, [_P, _L, _P, _I, _I, _P, _P, _P, _P]),
     ("b200_ivfpq_search_host", _I, [_P, _L, _P, _I, _I, _P, _P]),

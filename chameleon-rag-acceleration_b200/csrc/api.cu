@@ -11,6 +11,7 @@
 #include "../../include/b200_ivfpq.h"
 #include "kernels.cuh"
 #include "scan_skew.cuh"
+#include "coarse_tc.cuh"
 
 using namespace b200;
 
@@ -89,6 +90,12 @@ struct b200_ivfpq_index {
     // workspace
     DevBuf offsets, coarse_mat, probe32, hist, start, order, out_keys, out_cnt, qthr, stats, pq_t;
     DevBuf host_xq, host_D, host_I, tmp_list_no;
+    // tensor-core coarse quantizer (K1): split-bf16 centroids, norms, per-call buffers
+    DevBuf cent_bf16, cnorm, cmax2, q_bf16, qnorm, cand, cand_score, flags, nflagged;
+    CUtensorMap tmB;
+    bool tc_ready = false;
+    int coarse_variant = 0;   // 0 = auto (tensor cores when possible), 1 = exact kernels only
+    int kpad = 0;
     // instrumentation
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -113,11 +120,84 @@ int set_smem(K kernel, size_t bytes) {
 
 int grid1d(int64_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
 
+int tc_candidates(const b200_ivfpq_index* h, int nprobe) {
+    int64_t L = std::max<int64_t>(2 * (int64_t)nprobe, (int64_t)nprobe + 32);
+    return (int)std::min<int64_t>(L, 2048);
+}
+
+bool tc_usable(const b200_ivfpq_index* h, int nprobe) {
+    if (h->coarse_variant == 1 || !h->tc_ready) return false;
+    if (nprobe + 32 > 2048) return false;
+    return tc_candidates(h, nprobe) < h->nlist;   // otherwise every centroid would be a candidate anyway
+}
+
+// approximate scores s(q, c) = ||c||^2 - 2 q.c for one chunk of queries, on the tensor cores
+int run_tc_scores(b200_ivfpq_index* h, int64_t nq, const float* d_xq, float* d_scores, cudaStream_t st) {
+    int rc;
+    if ((rc = h->q_bf16.ensure(sizeof(__nv_bfloat16) * nq * h->kpad))) return rc;
+    if ((rc = h->qnorm.ensure(sizeof(float) * nq))) return rc;
+    tc_split_rows_kernel<<<(unsigned)nq, 128, 0, st>>>(d_xq, nq, h->d, h->kpad, 1, h->q_bf16.as<__nv_bfloat16>(),
+                                                      h->qnorm.as<float>());
+    LAUNCH_CHECK();
+    CUtensorMap tmA;
+    if (!tc_make_map(&tmA, h->q_bf16.p, nq, h->kpad, kTcBM))
+        return fail(B200_IVFPQ_ECUDA, "cuTensorMapEncodeTiled failed for the query operand");
+    TcGemmParams gp;
+    gp.cnorm = h->cnorm.as<float>();
+    gp.qnorm = h->qnorm.as<float>();
+    gp.out = d_scores;
+    gp.nq = nq;
+    gp.nlist = h->nlist;
+    gp.kblocks = h->kpad / kTcBK;
+    gp.mtiles = (int)((nq + kTcBM - 1) / kTcBM);
+    gp.ntiles = (int)((h->nlist + kTcBN - 1) / kTcBN);
+    CUDA_TRY(cudaFuncSetAttribute(coarse_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kTcSmemBytes));
+    int grid = std::min<int64_t>((int64_t)gp.mtiles * gp.ntiles, h->num_sms);
+    coarse_tc_gemm_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tmA, h->tmB, gp);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 // K1 for one chunk of queries: distances to all centroids, then nprobe-select.
 int run_coarse(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int nprobe, int32_t* probe32, int64_t* ids64,
                float* dis, cudaStream_t st, bool time_stages) {
     int rc = h->coarse_mat.ensure(sizeof(float) * nq * h->nlist);
     if (rc) return rc;
+    if (tc_usable(h, nprobe)) {
+        // tensor-core pre-filter + exact rescoring (coarse_tc.cuh)
+        const int L = tc_candidates(h, nprobe);
+        if ((rc = h->cand.ensure(sizeof(int32_t) * nq * L))) return rc;
+        if ((rc = h->cand_score.ensure(sizeof(float) * nq * L))) return rc;
+        if ((rc = h->flags.ensure(sizeof(int) * nq))) return rc;
+        if (!h->nflagged.p) {
+            if ((rc = h->nflagged.ensure(sizeof(int)))) return rc;
+            CUDA_TRY(cudaMemsetAsync(h->nflagged.p, 0, sizeof(int), st));
+        }
+        if ((rc = run_tc_scores(h, nq, d_xq, h->coarse_mat.as<float>(), st))) return rc;
+        if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+        size_t ssm = TopK::smem_bytes(L, kSelCap);
+        if ((rc = set_smem(coarse_select_kernel, ssm))) return rc;
+        coarse_select_kernel<<<(unsigned)nq, kThreads, ssm, st>>>(h->coarse_mat.as<float>(), h->nlist, h->nlist, L,
+                                                                 h->cand.as<int32_t>(), nullptr,
+                                                                 h->cand_score.as<float>());
+        LAUNCH_CHECK();
+        const float eps_rel = 6e-5f, eps_abs = (float)(h->d + 2) * 1.1920929e-7f;
+        size_t rsm = sizeof(float) * ((h->d + 3) & ~3) + TopK::smem_bytes(nprobe, 2048);
+        if ((rc = set_smem(coarse_rescore_kernel, rsm))) return rc;
+        coarse_rescore_kernel<<<(unsigned)nq, kRescoreThreads, rsm, st>>>(
+            d_xq, h->cent, h->qnorm.as<float>(), h->cmax2.as<float>(), h->cand.as<int32_t>(),
+            h->cand_score.as<float>(), L, h->d, h->nlist, nprobe, eps_rel, eps_abs, probe32, ids64, dis,
+            h->flags.as<int>());
+        LAUNCH_CHECK();
+        size_t fsm = sizeof(float) * ((h->d + 3) & ~3) + TopK::smem_bytes(nprobe, kSelCap);
+        if ((rc = set_smem(coarse_exact_flagged_kernel, fsm))) return rc;
+        coarse_exact_flagged_kernel<<<(unsigned)nq, kThreads, fsm, st>>>(d_xq, h->cent, h->flags.as<int>(), h->d,
+                                                                        h->nlist, nprobe, probe32, ids64, dis,
+                                                                        h->nflagged.as<int>());
+        LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid(static_cast<unsigned>((h->nlist + kCoarseTile - 1) / kCoarseTile),
               static_cast<unsigned>((nq + kCoarseTile - 1) / kCoarseTile));
     coarse_dist_kernel<<<grid, kThreads, 0, st>>>(d_xq, h->cent, h->coarse_mat.as<float>(), (int)nq, h->nlist, h->d,
@@ -319,6 +399,8 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     const char* v = getenv("B200_IVFPQ_SCAN");
     if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : 0;
+    v = getenv("B200_IVFPQ_COARSE");
+    if (v) h->coarse_variant = !strcmp(v, "exact") ? 1 : 0;
     *out = h;
     return 0;
 }
@@ -328,7 +410,8 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t,
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
-                      &h->host_D,  &h->host_I,     &h->tmp_list_no};
+                      &h->host_D,  &h->host_I,     &h->tmp_list_no, &h->cent_bf16, &h->cnorm, &h->cmax2,
+                      &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -341,6 +424,22 @@ int b200_ivfpq_set_codebooks(b200_ivfpq_t h, const float* d_centroids, const flo
     if (!d_centroids) return fail(B200_IVFPQ_EINVAL, "null centroid pointer");
     h->cent = d_centroids;
     h->pq = d_pq;
+    {   // K1 tensor-core operands: B' = [ch | cl | ch] (nlist, kpad) bf16, ||c||^2, max ||c||^2
+        CUDA_TRY(cudaSetDevice(h->device));
+        h->tc_ready = false;
+        h->kpad = tc_kpad(h->d);
+        int rc0;
+        if ((rc0 = h->cent_bf16.ensure(sizeof(__nv_bfloat16) * h->nlist * h->kpad))) return rc0;
+        if ((rc0 = h->cnorm.ensure(sizeof(float) * h->nlist))) return rc0;
+        if ((rc0 = h->cmax2.ensure(sizeof(float)))) return rc0;
+        tc_split_rows_kernel<<<(unsigned)h->nlist, 128>>>(d_centroids, h->nlist, h->d, h->kpad, 0,
+                                                          h->cent_bf16.as<__nv_bfloat16>(), h->cnorm.as<float>());
+        LAUNCH_CHECK();
+        tc_max_kernel<<<1, 256>>>(h->cnorm.as<float>(), h->nlist, h->cmax2.as<float>());
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaDeviceSynchronize());
+        h->tc_ready = tc_make_map(&h->tmB, h->cent_bf16.p, h->nlist, h->kpad, kTcBN);
+    }
     if (!d_pq) return 0;   // coarse-only handle (IndexFlatL2): b200_ivfpq_coarse works, search does not
     // m-fastest copy of the PQ codebook for the conflict-free scan kernel's LUT build
     CUDA_TRY(cudaSetDevice(h->device));
@@ -394,6 +493,28 @@ int b200_ivfpq_coarse(b200_ivfpq_t h, int64_t nq, const float* d_xq, int nprobe,
                             d_dis ? d_dis + q0 * nprobe : nullptr, st, false);
         if (rc) return rc;
     }
+    return 0;
+}
+
+int b200_ivfpq_coarse_scores(b200_ivfpq_t h, int64_t nq, const float* d_xq, float* d_scores, void* stream) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!h->cent) return fail(B200_IVFPQ_ESTATE, "index is not trained (set_codebooks not called)");
+    if (!h->tc_ready || h->coarse_variant == 1)
+        return fail(B200_IVFPQ_EUNSUPPORTED, "tensor-core coarse path is not available / disabled");
+    if (nq <= 0 || !d_xq || !d_scores) return fail(B200_IVFPQ_EINVAL, "bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return run_tc_scores(h, nq, d_xq, d_scores, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200_ivfpq_coarse_fallbacks(b200_ivfpq_t h, int64_t* h_count) {
+    if (!h || !h_count) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    *h_count = 0;
+    if (!h->nflagged.p) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    int v = 0;
+    CUDA_TRY(cudaMemcpy(&v, h->nflagged.p, sizeof(int), cudaMemcpyDeviceToHost));
+    *h_count = v;
     return 0;
 }
 

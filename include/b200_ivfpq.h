@@ -77,6 +77,13 @@ B200_API int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, cons
 B200_API int b200_ivfpq_coarse(b200_ivfpq_t h, int64_t nq, const float* d_xq, int nprobe, int64_t* d_ids, float* d_dis,
                       void* stream);
 
+/* K1 internals, exposed for tests and profiling: the tensor-core pre-filter scores s(q, c) = ||c||^2 - 2 q.c
+ * (tcgen05 split-bf16 GEMM) into d_scores (nq, nlist) f32, and the number of queries of all b200_ivfpq_coarse /
+ * search calls so far whose candidate set could not be proven sufficient and were redone by the exact kernels
+ * (synchronises the device).  coarse_scores returns B200_IVFPQ_EUNSUPPORTED when the tensor-core path is off. */
+B200_API int b200_ivfpq_coarse_scores(b200_ivfpq_t h, int64_t nq, const float* d_xq, float* d_scores, void* stream);
+B200_API int b200_ivfpq_coarse_fallbacks(b200_ivfpq_t h, int64_t* h_count);
+
 /* a1..a6 -- index.search(xq, k) with index.nprobe = nprobe (bench_cpu_performance.py:269,
  * faiss_retriever.py:254).  Outputs (nq, k): D f32 ascending, I i64. */
 B200_API int b200_ivfpq_search(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe, float* d_D, int64_t* d_I,
