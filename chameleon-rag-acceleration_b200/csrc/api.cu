@@ -5,7 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/b200_ivfpq.h"
@@ -19,6 +21,7 @@ namespace {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+std::atomic<uint64_t> g_ws_epoch{0};   // bumped whenever a workspace buffer is (re)allocated: invalidates CUDA graphs
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -52,6 +55,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
+        g_ws_epoch.fetch_add(1);
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
@@ -87,6 +91,7 @@ struct b200_ivfpq_index {
     bool has_lists = false;
     int device = 0, num_sms = 148;
     int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free)
+    int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
     // workspace
     DevBuf offsets, coarse_mat, probe32, hist, start, order, out_keys, out_cnt, qthr, stats, pq_t;
     DevBuf host_xq, host_D, host_I, tmp_list_no;
@@ -102,6 +107,20 @@ struct b200_ivfpq_index {
     float stage_ms[5] = {0, 0, 0, 0, 0};
     bool stage_valid = false;
     cudaStream_t last_stream = nullptr;
+    // small-batch latency path: the whole host-buffer search (H2D, kernels, D2H) replayed as a CUDA graph
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t epoch = 0;
+        int seen = 0;
+    };
+    std::map<std::tuple<int64_t, int, int>, GraphEntry> graphs;
+    cudaStream_t gstream = nullptr;
+    void* pin_xq = nullptr;
+    void* pin_D = nullptr;
+    void* pin_I = nullptr;
+    size_t pin_xq_cap = 0, pin_out_cap = 0;
+    uint64_t state_epoch = 0;   // bumped by set_codebooks / set_lists
+    int use_graph = 1;          // B200_IVFPQ_GRAPH=0 disables
 };
 
 namespace {
@@ -228,7 +247,7 @@ int launch_scan(b200_ivfpq_index* h, const ScanParams& sp, int64_t npairs, cudaS
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_pairs_kernel<VEC>, kThreads, smem));
     if (per_sm < 1) return fail(B200_IVFPQ_EUNSUPPORTED, "scan kernel does not fit (smem %zu B)", smem);
     int64_t grid = static_cast<int64_t>(per_sm) * h->num_sms;
-    if (grid > npairs) grid = npairs;
+    if (grid > npairs * sp.nseg) grid = npairs * sp.nseg;
     scan_pairs_kernel<VEC><<<(unsigned)grid, kThreads, smem, st>>>(sp);
     LAUNCH_CHECK();
     return 0;
@@ -263,14 +282,23 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     qb = std::min<int64_t>(qb, (int64_t)((1ll << 30) / nprobe));
     const bool single_chunk = qb >= nq;
 
+    // small batches: split every (query, probe) pair into nseg list segments so that the scan fills the GPU
+    int nseg = 1;
+    {
+        const int64_t pairs = std::min<int64_t>(qb, nq) * nprobe;
+        const int64_t target = 2 * (int64_t)h->num_sms;
+        if (pairs < target) nseg = (int)std::min<int64_t>(16, (target + pairs - 1) / pairs);
+        if (h->force_nseg > 0) nseg = h->force_nseg;
+    }
+
     int rc;
     if ((rc = h->stats.ensure(sizeof(PairStats)))) return rc;
     if ((rc = h->probe32.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
     if ((rc = h->hist.ensure(sizeof(int) * h->nlist))) return rc;
     if ((rc = h->start.ensure(sizeof(int) * h->nlist))) return rc;
     if ((rc = h->order.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
-    if ((rc = h->out_keys.ensure(sizeof(uint64_t) * qb * nprobe * k))) return rc;
-    if ((rc = h->out_cnt.ensure(sizeof(int) * qb * nprobe))) return rc;
+    if ((rc = h->out_keys.ensure(sizeof(uint64_t) * qb * nprobe * k * nseg))) return rc;
+    if ((rc = h->out_cnt.ensure(sizeof(int) * qb * nprobe * nseg))) return rc;
     if ((rc = h->qthr.ensure(sizeof(uint32_t) * qb))) return rc;
     CUDA_TRY(cudaMemsetAsync(h->stats.p, 0, sizeof(PairStats), st));
 
@@ -294,7 +322,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
 
         // pair setup
         CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * h->nlist, st));
-        CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs, st));
+        CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs * nseg, st));
         fill_u32_kernel<<<grid1d(nqc, 256), 256, 0, st>>>(h->qthr.as<uint32_t>(), nqc, kInfBits);
         LAUNCH_CHECK();
         PairStats* stats = h->stats.as<PairStats>();
@@ -326,6 +354,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.dsub = h->dsub;
         sp.nprobe = nprobe;
         sp.k = k;
+        sp.nseg = nseg;
         const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
         if (h->scan_variant == 2 && !use_skew)
@@ -353,7 +382,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if ((rc = set_smem(merge_query_kernel, msmem))) return rc;
         merge_query_kernel<<<(unsigned)nqc, kThreads, msmem, st>>>(h->out_keys.as<uint64_t>(), h->out_cnt.as<int>(),
                                                                   probe32, h->offsets.as<int64_t>(), h->ids, nprobe, k,
-                                                                  d_D + q0 * k, d_I + q0 * k);
+                                                                  nseg, d_D + q0 * k, d_I + q0 * k);
         LAUNCH_CHECK();
         if (tm) {
             CUDA_TRY(cudaEventRecord(h->ev[5], st));
@@ -399,6 +428,10 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     const char* v = getenv("B200_IVFPQ_SCAN");
     if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : 0;
+    v = getenv("B200_IVFPQ_GRAPH");
+    if (v) h->use_graph = atoi(v) != 0;
+    v = getenv("B200_IVFPQ_NSEG");
+    if (v) h->force_nseg = std::max(0, std::min(16, atoi(v)));
     v = getenv("B200_IVFPQ_COARSE");
     if (v) h->coarse_variant = !strcmp(v, "exact") ? 1 : 0;
     *out = h;
@@ -415,6 +448,12 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
     for (DevBuf* b : bufs) b->release();
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& kv : h->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (h->gstream) cudaStreamDestroy(h->gstream);
+    if (h->pin_xq) cudaFreeHost(h->pin_xq);
+    if (h->pin_D) cudaFreeHost(h->pin_D);
+    if (h->pin_I) cudaFreeHost(h->pin_I);
     delete h;
     return 0;
 }
@@ -424,6 +463,7 @@ int b200_ivfpq_set_codebooks(b200_ivfpq_t h, const float* d_centroids, const flo
     if (!d_centroids) return fail(B200_IVFPQ_EINVAL, "null centroid pointer");
     h->cent = d_centroids;
     h->pq = d_pq;
+    h->state_epoch++;
     {   // K1 tensor-core operands: B' = [ch | cl | ch] (nlist, kpad) bf16, ||c||^2, max ||c||^2
         CUDA_TRY(cudaSetDevice(h->device));
         h->tc_ready = false;
@@ -472,6 +512,7 @@ int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, const uint8_t
     h->ids = d_ids;
     h->ntotal = ntotal;
     h->has_lists = true;
+    h->state_epoch++;
     return 0;
 }
 
@@ -529,14 +570,98 @@ int b200_ivfpq_search_preassigned(b200_ivfpq_t h, int64_t nq, const float* d_xq,
     return search_impl(h, nq, d_xq, k, nprobe, d_list_ids, d_D, d_I, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int b200_ivfpq_search_host(b200_ivfpq_t h, int64_t nq, const float* h_xq, int k, int nprobe, float* h_D,
-                           int64_t* h_I) {
+namespace {
+
+constexpr int64_t kGraphMaxNq = 64;
+
+uint64_t graph_epoch(const b200_ivfpq_index* h) { return (h->state_epoch << 32) ^ g_ws_epoch.load(); }
+
+// H2D (pinned) -> search -> D2H (pinned) on h->gstream; enqueue only
+int enqueue_small_search(b200_ivfpq_index* h, int64_t nq, int k, int nprobe) {
+    cudaStream_t st = h->gstream;
+    CUDA_TRY(cudaMemcpyAsync(h->host_xq.p, h->pin_xq, sizeof(float) * nq * h->d, cudaMemcpyHostToDevice, st));
+    int rc = search_impl(h, nq, h->host_xq.as<float>(), k, nprobe, nullptr, h->host_D.as<float>(),
+                         h->host_I.as<int64_t>(), st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->pin_D, h->host_D.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->pin_I, h->host_I.p, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int search_host_small(b200_ivfpq_index* h, int64_t nq, const float* h_xq, int k, int nprobe, float* h_D,
+                      int64_t* h_I) {
+    if (!h->gstream) CUDA_TRY(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+    const size_t xq_bytes = sizeof(float) * kGraphMaxNq * h->d;
+    const size_t out_elems = (size_t)kGraphMaxNq * B200_IVFPQ_MAX_K;
+    if (h->pin_xq_cap < xq_bytes) {
+        if (h->pin_xq) cudaFreeHost(h->pin_xq);
+        CUDA_TRY(cudaMallocHost(&h->pin_xq, xq_bytes));
+        h->pin_xq_cap = xq_bytes;
+        g_ws_epoch.fetch_add(1);
+    }
+    if (h->pin_out_cap < out_elems) {
+        if (h->pin_D) cudaFreeHost(h->pin_D);
+        if (h->pin_I) cudaFreeHost(h->pin_I);
+        CUDA_TRY(cudaMallocHost(&h->pin_D, sizeof(float) * out_elems));
+        CUDA_TRY(cudaMallocHost(&h->pin_I, sizeof(int64_t) * out_elems));
+        h->pin_out_cap = out_elems;
+        g_ws_epoch.fetch_add(1);
+    }
+    int rc;
+    if ((rc = h->host_xq.ensure(xq_bytes))) return rc;
+    if ((rc = h->host_D.ensure(sizeof(float) * out_elems))) return rc;
+    if ((rc = h->host_I.ensure(sizeof(int64_t) * out_elems))) return rc;
+    memcpy(h->pin_xq, h_xq, sizeof(float) * nq * h->d);
+
+    auto& ge = h->graphs[std::make_tuple(nq, k, nprobe)];
+    if (ge.exec && ge.epoch == graph_epoch(h)) {
+        CUDA_TRY(cudaGraphLaunch(ge.exec, h->gstream));
+        h->last_stream = h->gstream;
+        CUDA_TRY(cudaStreamSynchronize(h->gstream));
+    } else {
+        if (ge.exec) {
+            cudaGraphExecDestroy(ge.exec);
+            ge.exec = nullptr;
+        }
+        if ((rc = enqueue_small_search(h, nq, k, nprobe))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(h->gstream));
+        if (++ge.seen >= 2) {
+            // workspace is sized by now: record the same sequence into a graph for the next calls
+            const uint64_t epoch0 = graph_epoch(h);
+            const bool timing = h->timing;
+            h->timing = false;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                int crc = enqueue_small_search(h, nq, k, nprobe);
+                cudaError_t e = cudaStreamEndCapture(h->gstream, &graph);
+                if (crc == 0 && e == cudaSuccess && graph && graph_epoch(h) == epoch0) {
+                    if (cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess) ge.epoch = epoch0;
+                    else ge.exec = nullptr;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();
+            h->timing = timing;
+        }
+    }
+    memcpy(h_D, h->pin_D, sizeof(float) * nq * k);
+    memcpy(h_I, h->pin_I, sizeof(int64_t) * nq * k);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int b200_ivfpq_search_host(b200_ivfpq_t h, int64_t nq, const float* h_xq, int k, int nprobe, float* h_D,
+                                      int64_t* h_I) {
     if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
     if (nq < 0) return fail(B200_IVFPQ_EINVAL, "nq < 0");
     if (nq == 0) return 0;
     if (!h_xq || !h_D || !h_I) return fail(B200_IVFPQ_EINVAL, "null host pointer");
     if (k < 1 || k > B200_IVFPQ_MAX_K) return fail(B200_IVFPQ_EINVAL, "k = %d out of [1, %d]", k, B200_IVFPQ_MAX_K);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->use_graph && nq <= kGraphMaxNq && h->cent && h->pq && h->has_lists && nprobe >= 1 &&
+        nprobe <= B200_IVFPQ_MAX_NPROBE)
+        return search_host_small(h, nq, h_xq, k, nprobe, h_D, h_I);
     int rc;
     if ((rc = h->host_xq.ensure(sizeof(float) * nq * h->d))) return rc;
     if ((rc = h->host_D.ensure(sizeof(float) * nq * k))) return rc;

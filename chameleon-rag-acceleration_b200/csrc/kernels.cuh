@@ -258,6 +258,8 @@ struct ScanParams {
     uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf
     PairStats* stats;
     int d, M, dsub, nprobe, k;
+    int nseg;                 // each (query, probe) pair is scanned by nseg CTAs (contiguous segments of its list):
+                              // fills the GPU at small batch sizes; slot = pair * nseg + segment
 };
 
 constexpr int kScanCap = 2048;
@@ -344,12 +346,21 @@ __global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p
         if (tid == 0) s_work = atomicAdd(&p.stats->work_counter, 1);
         __syncthreads();
         const int w = s_work;
-        if (w >= nvalid) break;
-        const int pair = p.order[w];
+        if (w >= nvalid * p.nseg) break;
+        const int pair = p.order[w / p.nseg];
+        const int seg = w % p.nseg;
+        const int slot = pair * p.nseg + seg;
         const int q = pair / p.nprobe;
         const int list = p.probe[pair];
         const int64_t beg = p.offsets[list];
-        const int64_t n = p.offsets[list + 1] - beg;
+        const int64_t ntot = p.offsets[list + 1] - beg;
+        const int64_t seglen = (((ntot + p.nseg - 1) / p.nseg) + 255) & ~static_cast<int64_t>(255);
+        const int64_t soff = seg * seglen;                        // first code of this segment
+        if (soff >= ntot) {                                       // empty segment: out_cnt stays 0
+            __syncthreads();
+            continue;
+        }
+        const int64_t n = min(seglen, ntot - soff);
 
         // a2: residual
         for (int j = tid; j < p.d; j += kThreads)
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p
         }
         __syncthreads();
         // a4 + a5
-        const uint8_t* lcodes = p.codes + beg * p.M;
+        const uint8_t* lcodes = p.codes + (beg + soff) * p.M;
         uint32_t thr = ext_thr;
         for (int64_t base = 0; base < n; base += kScanTile) {
 #pragma unroll
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p
                 int64_t i = base + u * kThreads + tid;
                 uint32_t bits = 0xffffffffu;
                 if (i < n) bits = __float_as_uint(adc_one<VEC>(lut, lcodes + i * p.M, p.M));
-                tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(i)));
+                tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(soff + i)));
             }
             tk.sync_and_flush_if_over<kThreads>(kScanCap - kScanTile, ext_thr);
             thr = tk.threshold();
@@ -385,9 +396,9 @@ __global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p
         tk.flush<kThreads>(ext_thr);
         const int nb = tk.count();
         const uint64_t* s = tk.sorted();
-        for (int i = tid; i < nb; i += kThreads) p.out_keys[static_cast<int64_t>(pair) * p.k + i] = s[i];
+        for (int i = tid; i < nb; i += kThreads) p.out_keys[static_cast<int64_t>(slot) * p.k + i] = s[i];
         if (tid == 0) {
-            p.out_cnt[pair] = nb;
+            p.out_cnt[slot] = nb;
             if (nb == p.k) atomicMin(p.qthr + q, static_cast<uint32_t>(s[p.k - 1] >> 32));
         }
         __syncthreads();   // smem reuse by the next pair
@@ -407,7 +418,8 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
                                                                const int32_t* __restrict__ probe,
                                                                const int64_t* __restrict__ offsets,
                                                                const int64_t* __restrict__ ids, int nprobe, int k,
-                                                               float* __restrict__ D, int64_t* __restrict__ I) {
+                                                               int nseg, float* __restrict__ D,
+                                                               int64_t* __restrict__ I) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TopK tk;
     tk.bind(smem_raw, k, kMergeCap);
@@ -416,7 +428,9 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
     if (tid == 0) tk.reset(kInfBits);
     __syncthreads();
     uint32_t thr = kInfBits;
-    const int64_t total = static_cast<int64_t>(nprobe) * k;
+    // slots of a query: (probe rank, segment) in scan order, so slot * k + j still orders like (rank, offset)
+    const int nslot = nprobe * nseg;
+    const int64_t total = static_cast<int64_t>(nslot) * k;
     for (int64_t base = 0; base < total; base += kMergeTile) {
 #pragma unroll
         for (int u = 0; u < kMergeTile / kThreads; u++) {
@@ -424,8 +438,8 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
             uint32_t bits = 0xffffffffu;
             if (c < total) {
                 int pr = static_cast<int>(c / k), j = static_cast<int>(c % k);
-                int64_t pair = q * nprobe + pr;
-                if (j < pair_cnt[pair]) bits = static_cast<uint32_t>(pair_keys[pair * k + j] >> 32);
+                int64_t slot = q * nslot + pr;
+                if (j < pair_cnt[slot]) bits = static_cast<uint32_t>(pair_keys[slot * k + j] >> 32);
             }
             tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
         }
@@ -442,9 +456,9 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
         if (i < nb) {
             uint32_t tag = static_cast<uint32_t>(s[i] & 0xffffffffu);
             int pr = tag / k, j = tag % k;
-            int64_t pair = q * nprobe + pr;
-            uint32_t off = static_cast<uint32_t>(pair_keys[pair * k + j] & 0xffffffffu);
-            int64_t pos = offsets[probe[pair]] + off;
+            int64_t slot = q * nslot + pr;
+            uint32_t off = static_cast<uint32_t>(pair_keys[slot * k + j] & 0xffffffffu);
+            int64_t pos = offsets[probe[q * nprobe + pr / nseg]] + off;
             id = ids ? ids[pos] : pos;
             dv = __uint_as_float(static_cast<uint32_t>(s[i] >> 32));
         }

@@ -128,13 +128,22 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         if (tid == 0) *s_work = atomicAdd(&p.stats->work_counter, 1);
         __syncthreads();
         const int wk = *s_work;
-        if (wk >= nvalid) break;
-        const int pair = p.order[wk];
+        if (wk >= nvalid * p.nseg) break;
+        const int pair = p.order[wk / p.nseg];
+        const int seg = wk % p.nseg;
+        const int slot = pair * p.nseg + seg;
         const int q = pair / p.nprobe;
         const int list = p.probe[pair];
         const int64_t beg = p.offsets[list];
-        const uint32_t n = static_cast<uint32_t>(p.offsets[list + 1] - beg);
-        const uint4* lp = reinterpret_cast<const uint4*>(p.codes + beg * M);
+        const uint32_t ntot = static_cast<uint32_t>(p.offsets[list + 1] - beg);
+        const uint32_t seglen = (((ntot + p.nseg - 1) / p.nseg) + 255u) & ~255u;
+        const uint32_t soff = seg * seglen;                           // first code of this segment
+        if (soff >= ntot) {                                           // empty segment: out_cnt stays 0
+            __syncthreads();
+            continue;
+        }
+        const uint32_t n = min(seglen, ntot - soff);
+        const uint4* lp = reinterpret_cast<const uint4*>(p.codes + (beg + soff) * M);
 
         // lane's code in block b is b*256 + tid.  Ring of four code registers: slot (b+1)%4 holds code b.
         // Issue the first loads before building the LUT so that they overlap it.
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         const float fin = skew_block16(lutb, CUR, NXT, ws2, ws1, bs, loff, keep, cap, acc);     \
         const uint32_t idx = base + TB * 256u - 256u; /* wraps past 2^32 for the prologue block */ \
         const uint32_t bits = __float_as_uint(fin);                                             \
-        tk.push(idx < n && bits <= thr, make_key(bits, idx));                                   \
+        tk.push(idx < n && bits <= thr, make_key(bits, soff + idx));                                   \
     }
 #pragma unroll
             for (int half = 0; half < kSkewTB / 4; half++) {
@@ -218,9 +227,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         tk.flush<kThreads>(ext_thr);
         const int nb = tk.count();
         const uint64_t* s = tk.sorted();
-        for (int i = tid; i < nb; i += kThreads) p.out_keys[static_cast<int64_t>(pair) * p.k + i] = s[i];
+        for (int i = tid; i < nb; i += kThreads) p.out_keys[static_cast<int64_t>(slot) * p.k + i] = s[i];
         if (tid == 0) {
-            p.out_cnt[pair] = nb;
+            p.out_cnt[slot] = nb;
             if (nb == p.k) atomicMin(p.qthr + q, static_cast<uint32_t>(s[p.k - 1] >> 32));
         }
         __syncthreads();
@@ -236,7 +245,7 @@ int launch_scan_skew_t(const ScanParams& sp, const float* pq_t, int64_t npairs, 
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess) return -1;
     if (per_sm < 1) return -1;
     int64_t grid = static_cast<int64_t>(per_sm) * num_sms;
-    if (grid > npairs) grid = npairs;
+    if (grid > npairs * sp.nseg) grid = npairs * sp.nseg;
     kernel<<<(unsigned)grid, kThreads, smem, st>>>(sp, pq_t);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }

@@ -219,3 +219,47 @@ def test_c1_shape_properties(oracle):
     _util.assert_bit_equal(I[sel], Ir, "I vs oracle")
     st = index.last_scan_stats()
     assert st["bytes"] == st["codes"] * M
+
+
+@pytest.mark.parametrize("M,d", [(16, 128), (8, 32)])
+def test_small_batches_graph_replay_and_segments(oracle, M, d):
+    """Batch-1 latency path: list segmentation (each pair split over several CTAs) and CUDA-graph replay of the
+    host-buffer search.  Repeated calls with DIFFERENT queries must keep matching the oracle, and an index update
+    must invalidate the recorded graph."""
+    a = _util.make_index_arrays(oracle, 77, d, 40, M, 30000)
+    index = _load(a)
+    index.nprobe = 7
+    for nq in (1, 3, 17):
+        for rep in range(4):                              # call 1-2: plain, call 3+: graph replay
+            xq = _util.make_queries(1000 * nq + rep, a, nq)
+            Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 7, 10)
+            D, I = index.search(xq, 10)
+            _util.assert_bit_equal(D, Dr, f"D nq={nq} rep={rep}")
+            _util.assert_bit_equal(I, Ir, f"I nq={nq} rep={rep}")
+    # mutate the index: new lists -> the graph recorded for (nq=1, k=10, nprobe=7) must not be replayed
+    b = _util.make_index_arrays(oracle, 78, d, 40, M, 9000)
+    index.set_codebooks(b["coarse"], b["pq"])
+    index.set_lists(b["offsets"], b["codes"], b["ids"])
+    xq = _util.make_queries(5, b, 1)
+    Dr, Ir = oracle.C.search(xq, b["coarse"], b["pq"], b["offsets"], b["codes"], b["ids"], 7, 10)
+    for rep in range(3):
+        D, I = index.search(xq, 10)
+        _util.assert_bit_equal(D, Dr, "D after update")
+        _util.assert_bit_equal(I, Ir, "I after update")
+
+
+@pytest.mark.parametrize("variant,nseg", [("skew", 3), ("skew", 16), ("generic", 5)])
+def test_forced_list_segmentation(oracle, variant, nseg):
+    a = _util.make_index_arrays(oracle, 21, 128, 24, 16, 26000, used_lists=20)
+    xq = _util.make_queries(4, a, 40)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 9, 25)
+    os.environ["B200_IVFPQ_NSEG"] = str(nseg)
+    try:
+        index = _load(a, variant)
+    finally:
+        del os.environ["B200_IVFPQ_NSEG"]
+    index.nprobe = 9
+    import torch
+    D, I = index.search(torch.from_numpy(xq).cuda(), 25)
+    _util.assert_bit_equal(D.cpu().numpy(), Dr, "D")
+    _util.assert_bit_equal(I.cpu().numpy(), Ir, "I")
