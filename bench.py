@@ -44,6 +44,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, for one) write to fd 1, so the real
+# stdout is kept aside for the JSON line and fd 1 is pointed at stderr for everything else.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def workload_name(cfg, args):
     nb, d, nlist, M, nprobe, k, nq = cfg
     return (f"{args.config}: {nb // 1_000_000}M x {d}, IVF{nlist},PQ{M}x8, nprobe={nprobe}, k={k}, "
@@ -179,7 +190,7 @@ def run_reference(args):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -449,7 +460,7 @@ def run_ours(args):
             "latency_batch1_ms_p50": lat_p50, "recall_at_10": recall, "stages_ms": stages,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_oracle": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "scan_skew.cuh"
 #include "coarse_tc.cuh"
+#include "select_radix.cuh"
 
 using namespace b200;
 
@@ -139,6 +140,19 @@ int set_smem(K kernel, size_t bytes) {
 
 int grid1d(int64_t n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
 
+// K1b: k smallest (distance, id) of every row of a (nq, n) matrix -- radix select, one CTA per row
+int launch_select(b200_ivfpq_index* h, const float* mat, int64_t nq, int64_t n, int k, int32_t* ids32, int64_t* ids64,
+                  float* dis, cudaStream_t st) {
+    const size_t smem = select_smem_bytes(k);
+    if (nq < 2 * (int64_t)h->num_sms) {
+        select_radix_kernel<1024><<<(unsigned)nq, 1024, smem, st>>>(mat, n, n, k, ids32, ids64, dis);
+    } else {
+        select_radix_kernel<256><<<(unsigned)nq, 256, smem, st>>>(mat, n, n, k, ids32, ids64, dis);
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int tc_candidates(const b200_ivfpq_index* h, int nprobe) {
     int64_t L = std::max<int64_t>(2 * (int64_t)nprobe, (int64_t)nprobe + 32);
     return (int)std::min<int64_t>(L, 2048);
@@ -195,12 +209,9 @@ int run_coarse(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int nprobe, i
         }
         if ((rc = run_tc_scores(h, nq, d_xq, h->coarse_mat.as<float>(), st))) return rc;
         if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
-        size_t ssm = TopK::smem_bytes(L, kSelCap);
-        if ((rc = set_smem(coarse_select_kernel, ssm))) return rc;
-        coarse_select_kernel<<<(unsigned)nq, kThreads, ssm, st>>>(h->coarse_mat.as<float>(), h->nlist, h->nlist, L,
-                                                                 h->cand.as<int32_t>(), nullptr,
-                                                                 h->cand_score.as<float>());
-        LAUNCH_CHECK();
+        if ((rc = launch_select(h, h->coarse_mat.as<float>(), nq, h->nlist, L, h->cand.as<int32_t>(), nullptr,
+                                h->cand_score.as<float>(), st)))
+            return rc;
         const float eps_rel = 6e-5f, eps_abs = (float)(h->d + 2) * 1.1920929e-7f;
         size_t rsm = sizeof(float) * ((h->d + 3) & ~3) + TopK::smem_bytes(nprobe, 2048);
         if ((rc = set_smem(coarse_rescore_kernel, rsm))) return rc;
@@ -223,13 +234,7 @@ int run_coarse(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int nprobe, i
                                                   h->nlist);
     LAUNCH_CHECK();
     if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
-    size_t smem = TopK::smem_bytes(nprobe, kSelCap);
-    rc = set_smem(coarse_select_kernel, smem);
-    if (rc) return rc;
-    coarse_select_kernel<<<(unsigned)nq, kThreads, smem, st>>>(h->coarse_mat.as<float>(), h->nlist, h->nlist, nprobe,
-                                                              probe32, ids64, dis);
-    LAUNCH_CHECK();
-    return 0;
+    return launch_select(h, h->coarse_mat.as<float>(), nq, h->nlist, nprobe, probe32, ids64, dis, st);
 }
 
 int64_t coarse_chunk(const b200_ivfpq_index* h) {
@@ -382,7 +387,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if ((rc = set_smem(merge_query_kernel, msmem))) return rc;
         merge_query_kernel<<<(unsigned)nqc, kThreads, msmem, st>>>(h->out_keys.as<uint64_t>(), h->out_cnt.as<int>(),
                                                                   probe32, h->offsets.as<int64_t>(), h->ids, nprobe, k,
-                                                                  nseg, d_D + q0 * k, d_I + q0 * k);
+                                                                  nseg, h->qthr.as<uint32_t>(), d_D + q0 * k, d_I + q0 * k);
         LAUNCH_CHECK();
         if (tm) {
             CUDA_TRY(cudaEventRecord(h->ev[5], st));

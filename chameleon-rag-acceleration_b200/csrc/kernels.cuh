@@ -418,16 +418,19 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
                                                                const int32_t* __restrict__ probe,
                                                                const int64_t* __restrict__ offsets,
                                                                const int64_t* __restrict__ ids, int nprobe, int k,
-                                                               int nseg, float* __restrict__ D,
-                                                               int64_t* __restrict__ I) {
+                                                               int nseg, const uint32_t* __restrict__ qthr,
+                                                               float* __restrict__ D, int64_t* __restrict__ I) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TopK tk;
     tk.bind(smem_raw, k, kMergeCap);
     const int tid = threadIdx.x;
     const int64_t q = blockIdx.x;
-    if (tid == 0) tk.reset(kInfBits);
+    // qthr[q] = smallest k-th-best distance any (probe, segment) of this query reached: an upper bound on the
+    // final k-th distance, so candidates above it (strictly) can be dropped before any sorting
+    const uint32_t ext_thr = qthr ? qthr[q] : kInfBits;
+    if (tid == 0) tk.reset(ext_thr);
     __syncthreads();
-    uint32_t thr = kInfBits;
+    uint32_t thr = ext_thr;
     // slots of a query: (probe rank, segment) in scan order, so slot * k + j still orders like (rank, offset)
     const int nslot = nprobe * nseg;
     const int64_t total = static_cast<int64_t>(nslot) * k;
@@ -443,11 +446,11 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
             }
             tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
         }
-        tk.sync_and_flush_if_over<kThreads>(kMergeCap - kMergeTile, kInfBits);
+        tk.sync_and_flush_if_over<kThreads>(kMergeCap - kMergeTile, ext_thr);
         thr = tk.threshold();
     }
     __syncthreads();
-    tk.flush<kThreads>(kInfBits);
+    tk.flush<kThreads>(ext_thr);
     const int nb = tk.count();
     const uint64_t* s = tk.sorted();
     for (int i = tid; i < k; i += kThreads) {
