@@ -342,11 +342,14 @@ __global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p
     const int tid = threadIdx.x;
     const int nvalid = p.stats->nvalid;
 
+    int next_work = 0;
+    if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
     for (;;) {
-        if (tid == 0) s_work = atomicAdd(&p.stats->work_counter, 1);
+        if (tid == 0) s_work = next_work;
         __syncthreads();
         const int w = s_work;
         if (w >= nvalid * p.nseg) break;
+        if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);   // prefetch the next work item
         const int pair = p.order[w / p.nseg];
         const int seg = w % p.nseg;
         const int slot = pair * p.nseg + seg;

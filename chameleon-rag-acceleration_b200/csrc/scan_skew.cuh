@@ -65,6 +65,43 @@ __device__ __forceinline__ float skew_lookup(const char* __restrict__ lutb, uint
     return *reinterpret_cast<const float*>(lutb + a + 4 * p);
 }
 
+// ---- LUT entry in packed fp32x2 arithmetic ------------------------------------------------------------------------
+// sub.rn.f32x2 / mul.rn.f32x2 round each half exactly like the scalar ops, so (r_j - p_j)^2 is bit-identical to
+// the oracle's; the accumulation stays scalar and sequential in j (FADD2 + FMUL2 + 2 FADD per two dimensions
+// instead of 6 scalar ops).  The parity tests compare every LUT-dependent distance bit for bit, which also guards
+// against the assembler contracting any of this into FMAs.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    return (static_cast<uint64_t>(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// T = sum_j (r_j - p_j)^2 for one (m, c) entry; p points at pq_t[c][0][m] (stride M between dimensions, so that the
+// 16 lanes with consecutive m read consecutive words), rr2 holds (r_j, r_j+1)
+template <int DSUB, int M>
+__device__ __forceinline__ float lut_entry_packed(const float* __restrict__ p, const uint64_t (&rr2)[DSUB / 2]) {
+    float pv[DSUB];
+#pragma unroll
+    for (int j = 0; j < DSUB; j++) pv[j] = __ldg(p + j * M);
+    float a = 0.0f;
+#pragma unroll
+    for (int j = 0; j < DSUB / 2; j++) {
+        const uint64_t d2 = sub_f32x2(rr2[j], pack_f32x2(pv[2 * j], pv[2 * j + 1]));
+        const uint64_t s2 = mul_f32x2(d2, d2);
+        a = __fadd_rn(a, __uint_as_float(static_cast<uint32_t>(s2)));
+        a = __fadd_rn(a, __uint_as_float(static_cast<uint32_t>(s2 >> 32)));
+    }
+    return a;
+}
+
 // One block = 16 lookups per lane over the byte window [r, r+16) of cur|nxt.  acc carries the partial sum of the
 // code the lane is on; the return value is the finished distance of the code that completed in this block.
 __device__ __forceinline__ float skew_block16(const char* __restrict__ lutb, const uint4& cur, const uint4& nxt,
@@ -124,11 +161,16 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
     const int lm = tid & (M - 1), lc0 = tid >> 4;
     const int copy0 = (lane >> 4) * 16;
 
+    // work items are pulled from a global counter; the fetch for the NEXT item is issued at the top of the current
+    // one so that the atomic's round trip to L2 overlaps the pair's work
+    int next_work = 0;
+    if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
     for (;;) {
-        if (tid == 0) *s_work = atomicAdd(&p.stats->work_counter, 1);
+        if (tid == 0) *s_work = next_work;
         __syncthreads();
         const int wk = *s_work;
         if (wk >= nvalid * p.nseg) break;
+        if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
         const int pair = p.order[wk / p.nseg];
         const int seg = wk % p.nseg;
         const int slot = pair * p.nseg + seg;
@@ -159,20 +201,14 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         if (tid == 0) tk.reset(ext_thr);
         __syncthreads();
         // a3: LUT with periodic rows lut[c][w] = T[w % 16][c], w < 64
-        if (DSUB) {
-            float rr[DSUB ? DSUB : 1];
+        if constexpr (DSUB != 0) {
+            uint64_t rr2[DSUB / 2];
 #pragma unroll
-            for (int j = 0; j < (DSUB ? DSUB : 1); j++) rr[j] = res[lm * DSUB + j];
+            for (int j = 0; j < DSUB / 2; j++) rr2[j] = pack_f32x2(res[lm * DSUB + 2 * j], res[lm * DSUB + 2 * j + 1]);
 #pragma unroll 4
             for (int i = 0; i < 16; i++) {
                 const int c = lc0 + 16 * i;
-                const float* pc = pq_t + static_cast<int64_t>(c) * (DSUB * M) + lm;
-                float pv[DSUB ? DSUB : 1];
-#pragma unroll
-                for (int j = 0; j < (DSUB ? DSUB : 1); j++) pv[j] = __ldg(pc + j * M);
-                float a = 0.0f;
-#pragma unroll
-                for (int j = 0; j < (DSUB ? DSUB : 1); j++) a = sqdiff_acc(a, rr[j], pv[j]);
+                const float a = lut_entry_packed<DSUB, M>(pq_t + static_cast<int64_t>(c) * (DSUB * M) + lm, rr2);
                 float* row = lut + c * kSkewRowWords + lm;
                 row[copy0] = a;
                 row[copy0 ^ 16] = a;
