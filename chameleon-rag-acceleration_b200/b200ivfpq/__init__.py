@@ -11,7 +11,7 @@ from ._lib import LIB_PATH, launch_count, load as load_library
 from .factory import GpuParameterSpace, ParameterSpace, index_factory
 from .index import METRIC_L2, IndexFlatL2, IndexIVFPQ, InvertedLists, ProductQuantizer
 from .io import read_index, write_index
-from .retriever import IndexScanner, LocalB200Retriever
+from .retriever import AsyncB200Retriever, IndexScanner, LocalB200Retriever
 from .shards import DistributedIndexIVFPQ, merge_shards, shard_index, shard_positions
 
 
@@ -34,5 +34,5 @@ def downcast_index(index):
 
 
 __all__ = ["IndexFlatL2", "IndexIVFPQ", "index_factory", "ParameterSpace", "GpuParameterSpace", "search_preassigned",
-           "read_index", "write_index", "LocalB200Retriever", "IndexScanner", "DistributedIndexIVFPQ", "shard_index",
+           "read_index", "write_index", "LocalB200Retriever", "AsyncB200Retriever", "IndexScanner", "DistributedIndexIVFPQ", "shard_index",
            "merge_shards", "METRIC_L2", "omp_set_num_threads", "vector_to_array", "downcast_index", "launch_count"]

@@ -82,3 +82,70 @@ class IndexScanner:
         list_IDs = np.array(I, dtype="int64")
         list_centroids = self.centroids[list_IDs.flatten()].reshape(nq, nprobe, self.dim)
         return list_IDs, list_centroids
+
+
+class AsyncB200Retriever(LocalB200Retriever):
+    """In-process replacement for ExternalRetriever's split send / recv protocol
+    (llm_inference_gpu/ralm/retriever/retriever.py:109-163), which the tik-tok decoder uses to overlap the retrieval
+    of micro-batch A with the decode of micro-batch B (ralm/ralm_tiktok.py:129-192, 226-233).
+
+    retrieve_send(query, k)  enqueues the search on a side CUDA stream and returns at once.  `query` may be the
+                             decoder's hidden state as a CUDA tensor: no D2H copy (ralm.py:110-111 copies to the
+                             CPU every retrieval step) and no TCP hop; the side stream first waits for the
+                             producer stream, so the hidden state is complete before it is read.
+    poll()                   non-blocking: True when the answer is ready (ExternalRetriever.poll polls a socket).
+    retrieve_recv(k)         returns (indices, distances) like ExternalRetriever.retrieve_recv.  CUDA tensors in ->
+                             CUDA tensors out, and the CALLER's stream waits on the event (no host sync);
+                             numpy in -> numpy out.
+    """
+
+    def __init__(self, index: IndexIVFPQ, default_k: Optional[int] = 10, nprobe: Optional[int] = 1,
+                 device: Optional[str] = "gpu"):
+        self._dev = index._device()
+        self._stream = torch.cuda.Stream(device=self._dev)
+        self._event = None
+        self._pending = None
+        self._as_numpy = False
+        super().__init__(index, default_k=default_k, nprobe=nprobe, device=device)   # runs the warm-up search
+
+    def retrieve_send(self, query, k: Optional[int] = None, nprobe: Optional[int] = None):
+        if self._pending is not None:
+            raise RuntimeError("retrieve_send called twice without retrieve_recv")
+        if k is None:
+            k = self.default_k
+        if nprobe is not None:
+            self.set_nprobe(nprobe)
+        self._as_numpy = not isinstance(query, torch.Tensor)
+        producer = torch.cuda.current_stream(self._dev)
+        ready = torch.cuda.Event()
+        ready.record(producer)
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ready)
+            if self._as_numpy:
+                q = torch.from_numpy(np.ascontiguousarray(query, np.float32)).to(self._dev, non_blocking=True)
+            else:
+                q = query.to(self._dev).float().contiguous()
+                q.record_stream(self._stream)
+            D, I = self.index.search(q, k)
+            self._event = torch.cuda.Event()
+            self._event.record(self._stream)
+        self._pending = (D, I, q)
+
+    def poll(self) -> bool:
+        return self._event is not None and self._event.query()
+
+    def retrieve_recv(self, k: Optional[int] = None):
+        if self._pending is None:
+            raise RuntimeError("retrieve_recv without a pending retrieve_send")
+        D, I, _ = self._pending
+        self._pending = None
+        if self._as_numpy:
+            self._event.synchronize()
+            return I.cpu().numpy(), D.cpu().numpy()
+        torch.cuda.current_stream(self._dev).wait_event(self._event)
+        return I, D
+
+    def retrieve(self, query, nprobe: Optional[int] = None, k: Optional[int] = None):
+        self.retrieve_send(query, k=k, nprobe=nprobe)
+        I, D = self.retrieve_recv(k)
+        return {"id": I, "dist": D}

@@ -170,3 +170,36 @@ def test_merge_shards_kernel_and_sharded_search(oracle):
     from b200ivfpq.shards import pack_results, unpack_results
     d2, i2 = unpack_results(pack_results(Ds[0], Is[0]))
     assert torch.equal(d2, Ds[0]) and torch.equal(i2, Is[0])
+
+
+def test_async_retriever_overlaps_a_decode_stream(oracle):
+    """retrieve_send / poll / retrieve_recv (retriever.py:109-163 protocol) on a side stream: the query is a CUDA
+    tensor produced on the caller's stream right before the send (like the decoder's hidden state), other work is
+    enqueued while the retrieval runs, and the answer matches the oracle."""
+    import torch
+    import b200ivfpq as faiss
+    a = _util.make_index_arrays(oracle, 41, 128, 32, 16, 20000)
+    index = faiss.IndexIVFPQ(faiss.IndexFlatL2(128), 128, 32, 16, 8)
+    index.set_codebooks(a["coarse"], a["pq"])
+    index.set_lists(a["offsets"], a["codes"], a["ids"])
+    r = faiss.AsyncB200Retriever(index, default_k=10, nprobe=6)
+    xq = _util.make_queries(9, a, 4)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 6, 10)
+    for step in range(3):
+        hidden = torch.from_numpy(xq).cuda() * 1.0          # produced on the current stream just before the send
+        r.retrieve_send(hidden, k=10)
+        w = torch.randn(2048, 2048, device="cuda")
+        y = w @ w                                            # "decode" work enqueued while the retrieval runs
+        with pytest.raises(RuntimeError):
+            r.retrieve_send(hidden, k=10)                    # one outstanding request, like the socket protocol
+        I, D = r.retrieve_recv(10)
+        torch.cuda.synchronize()
+        assert r.poll()
+        _util.assert_bit_equal(D.cpu().numpy(), Dr, "D")
+        _util.assert_bit_equal(I.cpu().numpy(), Ir, "I")
+        assert y.shape == (2048, 2048)
+    out = r.retrieve(xq, nprobe=6, k=10)                     # numpy in -> numpy out
+    _util.assert_bit_equal(out["id"], Ir)
+    _util.assert_bit_equal(out["dist"], Dr)
+    with pytest.raises(RuntimeError):
+        r.retrieve_recv(10)
