@@ -6,16 +6,36 @@ from __future__ import annotations
 
 import numpy as np
 
+from .faiss_io import parse_faiss_ivfpq, write_faiss_ivfpq
 from .index import IndexFlatL2, IndexIVFPQ
 
 
+def _is_faiss_file(fname: str) -> bool:
+    try:
+        with open(fname, "rb") as f:
+            return f.read(4) == b"IwPQ"
+    except OSError:
+        return False
+
+
 def write_index(index: IndexIVFPQ, fname: str) -> None:
+    """`.index` / `.faiss` names are written in Faiss's IwPQ container (faiss_io.py), anything else as .npz."""
+    if fname.endswith((".index", ".faiss")):
+        write_faiss_ivfpq(fname, index.to_arrays(), nprobe=index.nprobe)
+        return
     a = index.to_arrays() if index.is_trained else {}
     np.savez(fname if fname.endswith(".npz") else fname + ".npz", d=index.d, nlist=index.nlist, M=index.pq.M,
              nbits=index.pq.nbits, nprobe=index.nprobe, is_trained=index.is_trained, **a)
 
 
 def read_index(fname: str) -> IndexIVFPQ:
+    if _is_faiss_file(fname):
+        z = parse_faiss_ivfpq(fname)
+        index = IndexIVFPQ(IndexFlatL2(z["d"]), z["d"], z["nlist"], z["M"], z["nbits"])
+        index.nprobe = z["nprobe"]
+        index.set_codebooks(z["coarse"], z["pq"])
+        index.set_lists(z["offsets"], z["codes"], z["ids"])
+        return index
     z = np.load(fname if fname.endswith(".npz") else fname + ".npz")
     index = IndexIVFPQ(IndexFlatL2(int(z["d"])), int(z["d"]), int(z["nlist"]), int(z["M"]), int(z["nbits"]))
     index.nprobe = int(z["nprobe"])

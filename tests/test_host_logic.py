@@ -136,3 +136,22 @@ def test_uniform_reference_generator_matches_the_script():
     ref = np.random.random((1000, 16)).astype("float32")
     ref[:, 0] += np.arange(1000) / 1000.
     assert np.array_equal(xb, ref) and xq.shape == (10, 16) and xq.dtype == np.float32
+
+
+def test_faiss_container_roundtrip(oracle, tmp_path):
+    """IwPQ container (Faiss 1.7.x layout): writer -> parser round trip, both flat-storage variants, full and sparse
+    list-size tables.  Not a check against a Faiss binary (none is available): see faiss_io.py STATUS."""
+    from b200ivfpq.faiss_io import parse_faiss_ivfpq, write_faiss_ivfpq
+    for used, storage in [(None, "float"), (3, "bytes")]:
+        a = _util.make_index_arrays(oracle, 5, 32, 12, 8, 700, used_lists=used)
+        fn = os.path.join(tmp_path, f"toy_IVF12,PQ8_populated_{storage}.index")
+        write_faiss_ivfpq(fn, a, nprobe=7, flat_storage=storage)
+        raw = open(fn, "rb").read()
+        assert raw[:4] == b"IwPQ" and b"IxF2" in raw[:64] and b"ilar" in raw
+        assert (b"sprs" in raw) == (used is not None)
+        z = parse_faiss_ivfpq(fn)
+        assert (z["d"], z["nlist"], z["M"], z["nbits"], z["nprobe"]) == (32, 12, 8, 8, 7)
+        for key in ("coarse", "pq", "offsets", "codes", "ids"):
+            _util.assert_bit_equal(z[key], a[key], key)
+    with pytest.raises(RuntimeError):
+        parse_faiss_ivfpq(b"IxF2" + bytes(64))
