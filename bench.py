@@ -8,7 +8,7 @@
 A "step" is one pass of the hot path (coarse -> LUT -> ADC scan -> top-k [-> all-gather -> merge]) over one
 10 000-query batch.  Default workload at N = 1 is BASELINE.json configs[1]: 100M x 128, IVF8192,PQ16x8,
 nprobe = 32, k = 10 (fits one B200: 1.6 GB codes + 0.8 GB ids).  With N > 1 the same 100M database is sharded
-by add-order position modulo N (strong scaling: fixed database and batch, value = queries / time).
+by vector over the N GPUs (strong scaling: fixed database and batch, value = queries / time).
 
 Everything printed besides the JSON line goes to stderr.
 """
@@ -199,7 +199,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 def build_index(cfg, rank, world, device, dist, args):
     """Generate -> train -> assign/encode -> discard, chunk by chunk on the GPU.  Rank r
-    keeps add-order positions with pos % world == r.  Rank 0 also keeps exact ground truth for a query sample."""
+    keeps the 2M-vector chunks c with c % world == r.  Exact ground truth for a query sample is computed alongside."""
     import torch
 
     import b200ivfpq as faiss
@@ -209,6 +209,7 @@ def build_index(cfg, rank, world, device, dist, args):
     gen = ClusteredGenerator(d, ncentres=args.ncentres or max(16, nlist // 2), sigma=args.sigma,
                              device=device, seed=7, latent_dim=args.latent_dim, sigma_iso=args.sigma_iso)
     index = faiss.index_factory(d, f"IVF{nlist},PQ{M}x8")
+    index.cp_niter = args.kmeans_iters
     t0 = time.perf_counter()
     ntrain = min(nb, max(256000, 100 * nlist))            # bench_cpu_performance.py:77-90
     if rank == 0:
@@ -229,16 +230,18 @@ def build_index(cfg, rank, world, device, dist, args):
     t_train = time.perf_counter() - t0
 
     xq = gen.chunk(SEED_QUERY, 0, max(nq, 1))
-    ngt = min(args.gt_queries, xq.shape[0]) if rank == 0 else 0
+    ngt = min(args.gt_queries, xq.shape[0])
     gt_d = torch.full((ngt, 10), float("inf"), device=device)
     gt_i = torch.full((ngt, 10), -1, dtype=torch.int64, device=device)
     xq_gt = xq[:ngt]
     qn = (xq_gt * xq_gt).sum(1, keepdim=True)
 
+    # Sharding by vector: chunk c (2M consecutive vectors) lives on rank c % world, so every inverted list is spread
+    # over all GPUs and each rank only generates, encodes and ground-truths its own 1/world of the database.
     t0 = time.perf_counter()
     chunk = 1 << 21
     nchunks = (nb + chunk - 1) // chunk
-    for ci in range(nchunks):
+    for ci in range(rank, nchunks, world):
         n = min(chunk, nb - ci * chunk)
         x = gen.chunk(SEED_BASE, ci, n)
         pos0 = ci * chunk
@@ -251,18 +254,21 @@ def build_index(cfg, rank, world, device, dist, args):
             gt_d, sel = torch.topk(alld, 10, dim=1, largest=False)
             gt_i = torch.gather(alli, 1, sel)
             del dd
-        if world > 1:
-            first = (rank - pos0) % world
-            keep = torch.arange(first, n, world, device=device)
-            x = x[keep]
-            ids = keep + pos0
-        else:
-            ids = torch.arange(pos0, pos0 + n, device=device)
-        index.add_with_ids(x, ids)
+        index.add_with_ids(x, torch.arange(pos0, pos0 + n, device=device))
         del x
-        if rank == 0 and (ci % 10 == 0 or ci == nchunks - 1):
+        if rank == 0 and ((ci // world) % 10 == 0 or ci + world >= nchunks):
             torch.cuda.synchronize()
             log(f"[build] chunk {ci + 1}/{nchunks}  {time.perf_counter() - t0:.1f} s")
+    if world > 1 and ngt:
+        # merge the per-rank ground truth
+        all_d = torch.empty((world * ngt, 10), device=device)
+        all_i = torch.empty((world * ngt, 10), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(all_d, gt_d.contiguous())
+        dist.all_gather_into_tensor(all_i, gt_i.contiguous())
+        all_d = all_d.view(world, ngt, 10).permute(1, 0, 2).reshape(ngt, world * 10)
+        all_i = all_i.view(world, ngt, 10).permute(1, 0, 2).reshape(ngt, world * 10)
+        gt_d, sel = torch.topk(all_d, 10, dim=1, largest=False)
+        gt_i = torch.gather(all_i, 1, sel)
     index._sync_lists()
     torch.cuda.synchronize()
     t_add = time.perf_counter() - t0
@@ -449,7 +455,7 @@ def run_ours(args):
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32/u8", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, args), "sharding": f"by vector, position % {world}",
+            "config": {"workload": workload_name(cfg, args), "sharding": f"by vector: 2M-vector chunks round-robin over {world} GPU(s)",
                        "l2_policy": "inputs larger than L2 (codes %.0f MB per GPU vs 126 MB L2)" %
                                     (index.ntotal * M / 1e6),
                        "scan_kernel": os.environ.get("B200_IVFPQ_SCAN", "auto"), "ntotal_per_gpu": index.ntotal,
@@ -481,6 +487,7 @@ def main():
     ap.add_argument("--latent-dim", type=int, default=12)
     ap.add_argument("--ncentres", type=int, default=0)
     ap.add_argument("--gt-queries", type=int, default=1000)
+    ap.add_argument("--kmeans-iters", type=int, default=25, help="Lloyd iterations for index.train (Faiss default 25)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -11,8 +11,10 @@ from __future__ import annotations
 import torch
 
 
-def _assign(x: torch.Tensor, c: torch.Tensor, chunk: int = 1 << 18):
+def _assign(x: torch.Tensor, c: torch.Tensor, chunk: int = 0):
     """argmin_c ||x - c||^2 via ||c||^2 - 2 x.c ; returns (labels i64, sum of min distances)."""
+    if chunk <= 0:   # keep the (chunk, k) distance matrix around 1 GiB
+        chunk = max(1024, min(1 << 18, (1 << 28) // max(1, c.shape[0])))
     cn = (c * c).sum(1)
     labels = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
     obj = 0.0

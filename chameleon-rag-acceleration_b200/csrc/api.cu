@@ -95,7 +95,7 @@ struct b200_ivfpq_index {
     int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
     // workspace
     DevBuf offsets, coarse_mat, probe32, hist, start, order, out_keys, out_cnt, qthr, stats, pq_t;
-    DevBuf host_xq, host_D, host_I, tmp_list_no;
+    DevBuf host_xq, host_D, host_I;
     // tensor-core coarse quantizer (K1): split-bf16 centroids, norms, per-call buffers
     DevBuf cent_bf16, cnorm, cmax2, q_bf16, qnorm, cand, cand_score, flags, nflagged;
     CUtensorMap tmB;
@@ -105,7 +105,6 @@ struct b200_ivfpq_index {
     // instrumentation
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float stage_ms[5] = {0, 0, 0, 0, 0};
     bool stage_valid = false;
     cudaStream_t last_stream = nullptr;
     // small-batch latency path: the whole host-buffer search (H2D, kernels, D2H) replayed as a CUDA graph
@@ -448,7 +447,7 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t,
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
-                      &h->host_D,  &h->host_I,     &h->tmp_list_no, &h->cent_bf16, &h->cnorm, &h->cmax2,
+                      &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
                       &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : h->ev)

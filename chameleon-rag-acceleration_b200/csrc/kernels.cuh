@@ -1,6 +1,7 @@
 // kernels.cuh -- sm_100a kernels of the IVF-PQ search path.
 //
-//   K1  coarse_dist_kernel / coarse_select_kernel   a1  exact fp32 query x centroid L2^2, nprobe-select
+//   K1  coarse_dist_kernel (exact fp32 query x centroid L2^2; tensor-core path in coarse_tc.cuh, select in
+//       select_radix.cuh)                           a1
 //   K2+K3+K4  scan_pairs_kernel                      a2-a5 residual, LUT in shared memory, ADC scan, top-k
 //   K4b merge_query_kernel                           a5,a6 per-query merge over probes + id lookup
 //   K5  merge_shards_kernel                          multi-GPU merge after the all-gather
@@ -88,54 +89,9 @@ __global__ void __launch_bounds__(kThreads) coarse_dist_kernel(const float* __re
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K1b: per-query nprobe-select over a row of coarse distances.  One CTA per query.
-// Output ascending by (distance, centroid id) -- "sort, take nprobe" (ipynb:7997-7999).
-// ------------------------------------------------------------------------------------------------
+// K1b (per-query nprobe-select) lives in select_radix.cuh.  Tile / queue sizes of the exact fallback kernel:
 constexpr int kSelCap = 2048;
 constexpr int kSelTile = kThreads * 4;
-
-__global__ void __launch_bounds__(kThreads) coarse_select_kernel(const float* __restrict__ dist, int64_t nlist,
-                                                                 int64_t stride, int nprobe,
-                                                                 int32_t* __restrict__ probe32,
-                                                                 int64_t* __restrict__ ids64,
-                                                                 float* __restrict__ dis_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TopK tk;
-    tk.bind(smem_raw, nprobe, kSelCap);
-    const int tid = threadIdx.x;
-    const int64_t q = blockIdx.x;
-    const float* row = dist + q * stride;
-    if (tid == 0) tk.reset(kInfBits);
-    __syncthreads();
-    uint32_t thr = kInfBits;
-    for (int64_t base = 0; base < nlist; base += kSelTile) {
-#pragma unroll
-        for (int u = 0; u < kSelTile / kThreads; u++) {
-            int64_t c = base + u * kThreads + tid;
-            uint32_t bits = 0xffffffffu;
-            if (c < nlist) bits = __float_as_uint(row[c]);
-            tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
-        }
-        tk.sync_and_flush_if_over<kThreads>(kSelCap - kSelTile, kInfBits);
-        thr = tk.threshold();
-    }
-    __syncthreads();
-    tk.flush<kThreads>(kInfBits);
-    const int nb = tk.count();
-    const uint64_t* s = tk.sorted();
-    for (int i = tid; i < nprobe; i += kThreads) {
-        int32_t id = -1;
-        float dv = FLT_MAX;
-        if (i < nb) {
-            id = static_cast<int32_t>(s[i] & 0xffffffffu);
-            dv = __uint_as_float(static_cast<uint32_t>(s[i] >> 32));
-        }
-        if (probe32) probe32[q * nprobe + i] = id;
-        if (ids64) ids64[q * nprobe + i] = id;
-        if (dis_out) dis_out[q * nprobe + i] = dv;
-    }
-}
 
 // convert caller-provided int64 list ids (search_preassigned) to the internal int32 probe table
 __global__ void probes_from_i64_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
@@ -560,11 +516,6 @@ __global__ void __launch_bounds__(kThreads) encode_kernel(const float* __restric
         }
     }
     codes[i * M + m] = static_cast<uint8_t>(arg);
-}
-
-__global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
-    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i];
 }
 
 }  // namespace b200
