@@ -1,6 +1,7 @@
 // api.cu -- C-ABI (include/b200_ivfpq.h) and host-side orchestration of the search path.
 // One index handle owns only its workspace; codebooks and inverted lists are borrowed device pointers
 // (torch tensors on the Python side), so a populated index costs no extra HBM.
+#include <array>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -77,7 +78,7 @@ struct DevBuf {
     }
 };
 
-constexpr size_t kCoarseMatrixBudget = size_t(1) << 30;   // bytes of coarse distances per query chunk
+constexpr size_t kCoarseMatrixBudget = size_t(3) << 30;   // bytes of coarse distances per query chunk
 constexpr size_t kPairOutBudget = size_t(2) << 30;        // bytes of per-pair candidates per query chunk
 
 }  // namespace
@@ -104,7 +105,9 @@ struct b200_ivfpq_index {
     int kpad = 0;
     // instrumentation
     bool timing = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<std::array<cudaEvent_t, 6>> evs;   // one event set per query chunk of the last search
+    cudaEvent_t* ev = nullptr;                     // event set of the chunk being enqueued
+    int timed_chunks = 0;
     bool stage_valid = false;
     cudaStream_t last_stream = nullptr;
     // small-batch latency path: the whole host-buffer search (H2D, kernels, D2H) replayed as a CUDA graph
@@ -125,9 +128,12 @@ struct b200_ivfpq_index {
 
 namespace {
 
-int ensure_events(b200_ivfpq_index* h) {
-    for (auto& e : h->ev)
-        if (!e) CUDA_TRY(cudaEventCreate(&e));
+int ensure_events(b200_ivfpq_index* h, size_t nchunks) {
+    while (h->evs.size() < nchunks) {
+        std::array<cudaEvent_t, 6> set{};
+        for (auto& e : set) CUDA_TRY(cudaEventCreate(&e));
+        h->evs.push_back(set);
+    }
     return 0;
 }
 
@@ -272,11 +278,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     if (!d_list_ids && nprobe > h->nlist) nprobe = static_cast<int>(h->nlist);   // Faiss clamps nprobe to nlist
 
     const bool timing = h->timing;
-    if (timing) {
-        int rc = ensure_events(h);
-        if (rc) return rc;
-    }
     h->stage_valid = false;
+    h->timed_chunks = 0;
     h->last_stream = st;
 
     // query chunking keeps the workspace bounded
@@ -284,7 +287,10 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     if (!d_list_ids) qb = std::min<int64_t>(qb, coarse_chunk(h));
     qb = std::min<int64_t>(qb, std::max<int64_t>(1, (int64_t)(kPairOutBudget / (sizeof(uint64_t) * (size_t)nprobe * k))));
     qb = std::min<int64_t>(qb, (int64_t)((1ll << 30) / nprobe));
-    const bool single_chunk = qb >= nq;
+    if (timing) {
+        int rc0 = ensure_events(h, (size_t)((nq + qb - 1) / qb));
+        if (rc0) return rc0;
+    }
 
     // small batches: split every (query, probe) pair into nseg list segments so that the scan fills the GPU
     int nseg = 1;
@@ -310,7 +316,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         const int64_t nqc = std::min<int64_t>(qb, nq - q0);
         const int64_t npairs = nqc * nprobe;
         const float* xq = d_xq + q0 * h->d;
-        const bool tm = timing && single_chunk;
+        const bool tm = timing;
+        if (tm) h->ev = h->evs[h->timed_chunks].data();
         int32_t* probe32 = h->probe32.as<int32_t>();
 
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[0], st));
@@ -390,6 +397,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         LAUNCH_CHECK();
         if (tm) {
             CUDA_TRY(cudaEventRecord(h->ev[5], st));
+            h->timed_chunks++;
             h->stage_valid = true;
         }
     }
@@ -450,8 +458,9 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
                       &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
                       &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged};
     for (DevBuf* b : bufs) b->release();
-    for (auto& e : h->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto& set : h->evs)
+        for (auto& e : set)
+            if (e) cudaEventDestroy(e);
     for (auto& kv : h->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (h->gstream) cudaStreamDestroy(h->gstream);
@@ -731,9 +740,17 @@ int b200_ivfpq_set_stage_timing(b200_ivfpq_t h, int enable) {
 
 int b200_ivfpq_get_stage_ms(b200_ivfpq_t h, float* h_ms5) {
     if (!h || !h_ms5) return fail(B200_IVFPQ_EINVAL, "null pointer");
-    if (!h->stage_valid) return fail(B200_IVFPQ_ESTATE, "no timed single-chunk search recorded");
-    CUDA_TRY(cudaEventSynchronize(h->ev[5]));
-    for (int i = 0; i < 5; i++) CUDA_TRY(cudaEventElapsedTime(&h_ms5[i], h->ev[i], h->ev[i + 1]));
+    if (!h->stage_valid || h->timed_chunks == 0) return fail(B200_IVFPQ_ESTATE, "no timed search recorded");
+    for (int i = 0; i < 5; i++) h_ms5[i] = 0.0f;
+    for (int c = 0; c < h->timed_chunks; c++) {
+        auto& ev = h->evs[c];
+        CUDA_TRY(cudaEventSynchronize(ev[5]));
+        for (int i = 0; i < 5; i++) {
+            float ms = 0.0f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            h_ms5[i] += ms;
+        }
+    }
     return 0;
 }
 
