@@ -14,6 +14,7 @@
 #include "../../include/b200_ivfpq.h"
 #include "kernels.cuh"
 #include "scan_skew.cuh"
+#include "scan_duo.cuh"
 #include "coarse_tc.cuh"
 #include "select_radix.cuh"
 
@@ -92,10 +93,10 @@ struct b200_ivfpq_index {
     const int64_t* ids = nullptr;
     bool has_lists = false;
     int device = 0, num_sms = 148;
-    int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free)
+    int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free), 3 = two-query skewed (scan_duo.cuh)
     int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
     // workspace
-    DevBuf offsets, coarse_mat, probe32, hist, start, order, out_keys, out_cnt, qthr, stats, pq_t;
+    DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t;
     DevBuf host_xq, host_D, host_I;
     // tensor-core coarse quantizer (K1): split-bf16 centroids, norms, per-call buffers
     DevBuf cent_bf16, cnorm, cmax2, q_bf16, qnorm, cand, cand_score, flags, nflagged;
@@ -306,6 +307,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     if ((rc = h->probe32.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
     if ((rc = h->hist.ensure(sizeof(int) * h->nlist))) return rc;
     if ((rc = h->start.ensure(sizeof(int) * h->nlist))) return rc;
+    if ((rc = h->gstart.ensure(sizeof(int) * h->nlist))) return rc;
+    if ((rc = h->groups.ensure(sizeof(int2) * qb * nprobe))) return rc;
     if ((rc = h->order.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
     if ((rc = h->out_keys.ensure(sizeof(uint64_t) * qb * nprobe * k * nseg))) return rc;
     if ((rc = h->out_cnt.ensure(sizeof(int) * qb * nprobe * nseg))) return rc;
@@ -340,10 +343,13 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         pair_hist_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
                                                              h->hist.as<int>(), stats);
         LAUNCH_CHECK();
-        pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->nlist, stats);
+        pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), h->nlist, stats);
         LAUNCH_CHECK();
+        CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, sizeof(int2) * npairs, st));
         pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
-                                                                h->start.as<int>(), h->order.as<int32_t>());
+                                                                h->start.as<int>(), h->gstart.as<int>(),
+                                                                h->hist.as<int>(), h->order.as<int32_t>(),
+                                                                h->groups.as<int2>());
         LAUNCH_CHECK();
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));
 
@@ -356,6 +362,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.codes = h->codes;
         sp.probe = probe32;
         sp.order = h->order.as<int32_t>();
+        sp.groups = h->groups.as<int2>();
         sp.out_keys = h->out_keys.as<uint64_t>();
         sp.out_cnt = h->out_cnt.as<int>();
         sp.qthr = h->qthr.as<uint32_t>();
@@ -368,9 +375,19 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.nseg = nseg;
         const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
-        if (h->scan_variant == 2 && !use_skew)
+        if (h->scan_variant >= 2 && !use_skew)
             return fail(B200_IVFPQ_EUNSUPPORTED, "skewed scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
-        if (use_skew) {
+        // two queries per work item pay off once lists are shared: on average >= 3 probing queries per list
+        bool use_duo = use_skew && nseg == 1 && h->scan_variant != 2 &&
+                       (h->scan_variant == 3 || npairs >= 3 * h->nlist);
+        if (use_duo) {
+            if ((rc = launch_scan_duo(sp, h->pq_t.as<float>(), npairs, h->num_sms, st))) {
+                if (rc == -1) return fail(B200_IVFPQ_ECUDA, "two-query scan launch failed: %s",
+                                          cudaGetErrorString(cudaGetLastError()));
+                return rc;
+            }
+            g_launches.fetch_add(1);
+        } else if (use_skew) {
             if ((rc = launch_scan_skew(sp, h->pq_t.as<float>(), npairs, h->num_sms, st))) {
                 if (rc == -1) return fail(B200_IVFPQ_ECUDA, "skewed scan launch failed: %s",
                                           cudaGetErrorString(cudaGetLastError()));
@@ -439,7 +456,7 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     CUDA_TRY(cudaGetDevice(&h->device));
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     const char* v = getenv("B200_IVFPQ_SCAN");
-    if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : 0;
+    if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : !strcmp(v, "duo") ? 3 : 0;
     v = getenv("B200_IVFPQ_GRAPH");
     if (v) h->use_graph = atoi(v) != 0;
     v = getenv("B200_IVFPQ_NSEG");
@@ -453,7 +470,7 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
 int b200_ivfpq_destroy(b200_ivfpq_t h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t,
+    DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t, &h->gstart, &h->groups,
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
                       &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
                       &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged};

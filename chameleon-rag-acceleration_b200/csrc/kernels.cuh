@@ -112,6 +112,7 @@ struct PairStats {
     unsigned long long scan_codes;   // sum over valid pairs of list_size
     int nvalid;                      // number of pairs with a non-empty list
     int work_counter;                // dynamic scheduler of scan_pairs_kernel
+    int ngroups;                     // number of same-list pair groups (scan_duo.cuh), sum over lists of ceil(cnt / 2)
 };
 
 __global__ void pair_hist_kernel(const int32_t* __restrict__ probe, int64_t npairs,
@@ -134,55 +135,88 @@ __global__ void pair_hist_kernel(const int32_t* __restrict__ probe, int64_t npai
     if ((threadIdx.x & 31) == 0 && codes) atomicAdd(&stats->scan_codes, codes);
 }
 
-// exclusive scan of hist[nlist] -> start[nlist]; single CTA (nlist <= a few 100k)
-__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ hist, int* __restrict__ start,
-                                                         int64_t nlist, PairStats* __restrict__ stats) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
+// exclusive scans of hist[nlist] -> start[nlist] (pairs) and of ceil(hist / 2) -> gstart[nlist] (two-query groups);
+// hist is zeroed on the way out so that pair_scatter_kernel can use it as its per-list cursor.
+// Single CTA (nlist <= a few 100k).
+__global__ void __launch_bounds__(1024) pair_scan_kernel(int* __restrict__ hist, int* __restrict__ start,
+                                                         int* __restrict__ gstart, int64_t nlist,
+                                                         PairStats* __restrict__ stats) {
+    __shared__ int warp_sums[32], warp_gsums[32];
+    __shared__ int carry, gcarry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry = 0;
+    if (tid == 0) {
+        carry = 0;
+        gcarry = 0;
+    }
     __syncthreads();
     for (int64_t base = 0; base < nlist; base += 1024) {
         int64_t i = base + tid;
         int v = i < nlist ? hist[i] : 0;
-        int x = v;
+        int gv = (v + 1) >> 1;
+        int x = v, gx = gv;
         for (int o = 1; o < 32; o <<= 1) {
             int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            int gy = __shfl_up_sync(0xffffffffu, gx, o);
+            if (lane >= o) {
+                x += y;
+                gx += gy;
+            }
         }
-        if (lane == 31) warp_sums[wid] = x;
+        if (lane == 31) {
+            warp_sums[wid] = x;
+            warp_gsums[wid] = gx;
+        }
         __syncthreads();
         if (wid == 0) {
-            int w = warp_sums[lane];
+            int w = warp_sums[lane], gw = warp_gsums[lane];
             for (int o = 1; o < 32; o <<= 1) {
                 int y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
+                int gy = __shfl_up_sync(0xffffffffu, gw, o);
+                if (lane >= o) {
+                    w += y;
+                    gw += gy;
+                }
             }
             warp_sums[lane] = w;
+            warp_gsums[lane] = gw;
         }
         __syncthreads();
         int prefix = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
-        if (i < nlist) start[i] = prefix;
+        int gprefix = gcarry + (wid ? warp_gsums[wid - 1] : 0) + gx - gv;
+        if (i < nlist) {
+            start[i] = prefix;
+            gstart[i] = gprefix;
+            hist[i] = 0;
+        }
         __syncthreads();
-        if (tid == 1023) carry = prefix + v;
+        if (tid == 1023) {
+            carry = prefix + v;
+            gcarry = gprefix + gv;
+        }
         __syncthreads();
     }
     if (tid == 0) {
         stats->nvalid = carry;
+        stats->ngroups = gcarry;
         stats->work_counter = 0;
     }
 }
 
+// order[] = pair indices sorted by list; groups[] = the same pairs two by two (groups is pre-filled with -1, so the
+// odd pair of a list keeps y = -1).  Which queries end up together depends on the atomics' order; results do not.
 __global__ void pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t npairs,
-                                    const int64_t* __restrict__ offsets, int* __restrict__ cursor,
-                                    int32_t* __restrict__ order) {
+                                    const int64_t* __restrict__ offsets, const int* __restrict__ start,
+                                    const int* __restrict__ gstart, int* __restrict__ cursor,
+                                    int32_t* __restrict__ order, int2* __restrict__ groups) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     int l = probe[i];
     if (l < 0) return;
     if (offsets[l + 1] - offsets[l] <= 0) return;
-    int pos = atomicAdd(&cursor[l], 1);
-    order[pos] = static_cast<int32_t>(i);
+    const int rank = atomicAdd(&cursor[l], 1);
+    order[start[l] + rank] = static_cast<int32_t>(i);
+    int* g = reinterpret_cast<int*>(groups + gstart[l] + (rank >> 1));
+    g[rank & 1] = static_cast<int32_t>(i);
 }
 
 __global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t v) {
@@ -209,6 +243,7 @@ struct ScanParams {
     const uint8_t* codes;     // (ntotal, M)
     const int32_t* probe;     // (nq * nprobe) list id or -1
     const int32_t* order;     // (nvalid) pair indices sorted by list
+    const int2* groups;       // (ngroups) pairs of the same list two by two, y = -1 for an odd one (scan_duo.cuh)
     uint64_t* out_keys;       // (nq * nprobe, k)
     int* out_cnt;             // (nq * nprobe), pre-zeroed
     uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf

@@ -71,7 +71,7 @@ def test_search_bit_exact(oracle, d, nlist, M, n, nq, nprobe, k, used):
     _util.assert_bit_equal(It.cpu().numpy(), Ir, "I (device path)")
 
 
-@pytest.mark.parametrize("variant", ["generic", "skew"])
+@pytest.mark.parametrize("variant", ["generic", "skew", "duo"])
 def test_both_scan_kernels_agree_with_oracle(oracle, variant):
     a = _util.make_index_arrays(oracle, 5, 128, 48, 16, 30000)
     xq = _util.make_queries(8, a, 50)
@@ -83,7 +83,7 @@ def test_both_scan_kernels_agree_with_oracle(oracle, variant):
     _util.assert_bit_equal(I, Ir, f"I ({variant})")
 
 
-@pytest.mark.parametrize("variant", ["generic", "skew"])
+@pytest.mark.parametrize("variant", ["generic", "skew", "duo"])
 def test_ties_follow_scan_order(oracle, variant):
     """Many duplicate codes -> equal distances; (distance, probe rank, offset) order must match the oracle."""
     rng = np.random.default_rng(3)
@@ -98,6 +98,26 @@ def test_ties_follow_scan_order(oracle, variant):
     D, I = index.search(xq, 50)
     _util.assert_bit_equal(D, Dr, "D")
     _util.assert_bit_equal(I, Ir, "I")
+
+
+@pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used", [
+    (128, 24, 30000, 101, 5, 10, None),     # odd numbers of queries per list: groups with a missing second query
+    (96, 16, 12000, 64, 16, 100, 13),       # dsub 6, k = 100, empty lists, every query probes every list
+    (64, 8, 3000, 1, 8, 10, None),          # one query: every group is a single
+    (256, 12, 5000, 37, 3, 7, None),        # dsub 16
+    (80, 12, 5000, 40, 4, 10, None),        # dsub 5: generic LUT build
+])
+def test_two_query_scan_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
+    """scan_duo.cuh: two queries of the same list per work item; results must not depend on the grouping."""
+    a = _util.make_index_arrays(oracle, 40 + d, d, nlist, 16, n, used_lists=used)
+    xq = _util.make_queries(11, a, nq)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+    index = _load(a, "duo")
+    index.nprobe = nprobe
+    for _ in range(2):          # the pairing of queries depends on atomics' order; the results must not
+        D, I = index.search(xq, k)
+        _util.assert_bit_equal(D, Dr, "D (duo)")
+        _util.assert_bit_equal(I, Ir, "I (duo)")
 
 
 def test_search_preassigned(oracle):
