@@ -308,7 +308,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     if ((rc = h->hist.ensure(sizeof(int) * h->nlist))) return rc;
     if ((rc = h->start.ensure(sizeof(int) * h->nlist))) return rc;
     if ((rc = h->gstart.ensure(sizeof(int) * h->nlist))) return rc;
-    if ((rc = h->groups.ensure(sizeof(int2) * qb * nprobe))) return rc;
+    if ((rc = h->groups.ensure(sizeof(DuoGroup) * qb * nprobe))) return rc;
     if ((rc = h->order.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
     if ((rc = h->out_keys.ensure(sizeof(uint64_t) * qb * nprobe * k * nseg))) return rc;
     if ((rc = h->out_cnt.ensure(sizeof(int) * qb * nprobe * nseg))) return rc;
@@ -345,11 +345,11 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         LAUNCH_CHECK();
         pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), h->nlist, stats);
         LAUNCH_CHECK();
-        CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, sizeof(int2) * npairs, st));
+        CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, sizeof(DuoGroup) * npairs, st));
         pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
                                                                 h->start.as<int>(), h->gstart.as<int>(),
                                                                 h->hist.as<int>(), h->order.as<int32_t>(),
-                                                                h->groups.as<int2>());
+                                                                h->groups.as<DuoGroup>());
         LAUNCH_CHECK();
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));
 
@@ -362,7 +362,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.codes = h->codes;
         sp.probe = probe32;
         sp.order = h->order.as<int32_t>();
-        sp.groups = h->groups.as<int2>();
+        sp.groups = h->groups.as<DuoGroup>();
         sp.out_keys = h->out_keys.as<uint64_t>();
         sp.out_cnt = h->out_cnt.as<int>();
         sp.qthr = h->qthr.as<uint32_t>();

@@ -202,21 +202,42 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(int* __restrict__ hist,
     }
 }
 
-// order[] = pair indices sorted by list; groups[] = the same pairs two by two (groups is pre-filled with -1, so the
-// odd pair of a list keeps y = -1).  Which queries end up together depends on the atomics' order; results do not.
+// One work item of the two-query scan (scan_duo.cuh): two (query, probe) pairs of the same list plus everything the
+// kernel needs to start on it, so that it is one 32-byte load away (no groups -> probe -> offsets pointer chase).
+struct __align__(16) DuoGroup {
+    int pair_a;
+    int pair_b;     // -1: the list had an odd number of probing queries
+    int list;
+    uint32_t n;     // list length (> 0)
+    int64_t beg;    // first row of the list in codes / ids
+    int64_t pad_;
+};
+static_assert(sizeof(DuoGroup) == 32, "DuoGroup is two 16-byte words");
+
+// order[] = pair indices sorted by list; groups[] = the same pairs two by two (pair_b is pre-set to -1 by a 0xff
+// memset, so the odd pair of a list keeps it).  Which queries end up together depends on the atomics' order; the
+// results do not.
 __global__ void pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t npairs,
                                     const int64_t* __restrict__ offsets, const int* __restrict__ start,
                                     const int* __restrict__ gstart, int* __restrict__ cursor,
-                                    int32_t* __restrict__ order, int2* __restrict__ groups) {
+                                    int32_t* __restrict__ order, DuoGroup* __restrict__ groups) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     int l = probe[i];
     if (l < 0) return;
-    if (offsets[l + 1] - offsets[l] <= 0) return;
+    const int64_t beg = offsets[l], sz = offsets[l + 1] - beg;
+    if (sz <= 0) return;
     const int rank = atomicAdd(&cursor[l], 1);
     order[start[l] + rank] = static_cast<int32_t>(i);
-    int* g = reinterpret_cast<int*>(groups + gstart[l] + (rank >> 1));
-    g[rank & 1] = static_cast<int32_t>(i);
+    DuoGroup* g = groups + gstart[l] + (rank >> 1);
+    if (rank & 1) {
+        g->pair_b = static_cast<int32_t>(i);
+    } else {
+        g->pair_a = static_cast<int32_t>(i);
+        g->list = l;
+        g->n = static_cast<uint32_t>(sz);
+        g->beg = beg;
+    }
 }
 
 __global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t v) {
@@ -243,7 +264,7 @@ struct ScanParams {
     const uint8_t* codes;     // (ntotal, M)
     const int32_t* probe;     // (nq * nprobe) list id or -1
     const int32_t* order;     // (nvalid) pair indices sorted by list
-    const int2* groups;       // (ngroups) pairs of the same list two by two, y = -1 for an odd one (scan_duo.cuh)
+    const DuoGroup* groups;   // (ngroups) work items of the two-query scan (scan_duo.cuh)
     uint64_t* out_keys;       // (nq * nprobe, k)
     int* out_cnt;             // (nq * nprobe), pre-zeroed
     uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf

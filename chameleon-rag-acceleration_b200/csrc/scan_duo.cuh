@@ -38,7 +38,8 @@ inline bool duo_supported(int M, int d, int k) {
 }
 
 __host__ __device__ inline size_t duo_smem_bytes(int d, int k) {
-    return kDuoLutBytes + 2 * sizeof(float) * static_cast<size_t>((d + 3) & ~3) + 2 * TopK::smem_bytes(k, kDuoCap) + 16;
+    return kDuoLutBytes + 2 * sizeof(float) * static_cast<size_t>((d + 3) & ~3) + 2 * TopK::smem_bytes(k, kDuoCap) + 16 +
+           2 * sizeof(DuoGroup);
 }
 
 __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
@@ -84,6 +85,14 @@ __device__ __forceinline__ uint64_t duo_block16(const char* __restrict__ lutb, c
     return fin;
 }
 
+// 32-byte descriptor, global -> shared, asynchronously (LDGSTS); completion: cp.async.wait_all + barrier
+__device__ __forceinline__ void duo_copy_group_async(DuoGroup* dst, const DuoGroup* src) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const char*>(src) + 16)
+                 : "memory");
+}
+
 template <int DSUB>
 __device__ __forceinline__ float lut_entry_regs(const float (&pv)[DSUB], const uint64_t (&rr2)[DSUB / 2]) {
     float a = 0.0f;
@@ -96,6 +105,11 @@ __device__ __forceinline__ float lut_entry_regs(const float (&pv)[DSUB], const u
     }
     return a;
 }
+
+// NOTE on packed arithmetic: ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 (even with
+// -fmad=false), which would break bit-parity with the oracle's separately rounded multiply and add.  The LUT entry
+// therefore packs the subtract and the multiply only and accumulates with scalar adds (lut_entry_regs); the parity
+// tests compare every distance bit for bit and caught exactly this when it was tried.
 
 // DSUB = d / 16 when it is one of the specialised values (residual slices held in registers), 0 = generic.
 template <int DSUB>
@@ -131,22 +145,32 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
     // lm = 0..15) stores 16 consecutive 8-byte entries: conflict-free
     const int lm = tid & (M - 1), lc0 = tid >> 4;
 
-    int next_work = 0;
-    if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
+    // Work items are pulled from a global counter, two ahead: the counter value for item i+1 is fetched at the top of
+    // item i, and once it has arrived (after the LUT build) thread 0 starts an asynchronous copy of that item's
+    // descriptor into shared memory, so that the next iteration starts without a dependent global load.
+    DuoGroup* s_grp = reinterpret_cast<DuoGroup*>(s_work + 4);   // [2], 16-byte aligned
+    int next_work = 0, buf = 0;
+    if (tid == 0) {
+        next_work = atomicAdd(&p.stats->work_counter, 1);
+        if (next_work < ngroups) duo_copy_group_async(&s_grp[0], p.groups + next_work);
+    }
     for (;;) {
-        if (tid == 0) *s_work = next_work;
+        if (tid == 0) {
+            *s_work = next_work;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
         __syncthreads();
         const int wk = *s_work;
         if (wk >= ngroups) break;
         if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
-        const int2 grp = p.groups[wk];
-        const int pair_a = grp.x;
-        const bool has_b = grp.y >= 0;
-        const int pair_b = has_b ? grp.y : grp.x;
+        const DuoGroup grp = s_grp[buf];
+        const int pair_a = grp.pair_a;
+        const bool has_b = grp.pair_b >= 0;
+        const int pair_b = has_b ? grp.pair_b : grp.pair_a;
         const int qa = pair_a / p.nprobe, qb = pair_b / p.nprobe;
-        const int list = p.probe[pair_a];
-        const int64_t beg = p.offsets[list];
-        const uint32_t n = static_cast<uint32_t>(p.offsets[list + 1] - beg);   // > 0: empty lists form no groups
+        const int list = grp.list;
+        const int64_t beg = grp.beg;
+        const uint32_t n = grp.n;                                 // > 0: empty lists form no groups
         const uint32_t n_b = has_b ? n : 0u;
         const uint4* lp = reinterpret_cast<const uint4*>(p.codes + beg * M);
 
@@ -208,32 +232,33 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
             }
         }
         __syncthreads();
+        buf ^= 1;
+        if (tid == 0 && next_work < ngroups) duo_copy_group_async(&s_grp[buf], p.groups + next_work);
 
         // a4 + a5.  Iteration `it` processes block b = it - 1 (it = 0 is the prologue that only feeds bytes
         // 0..r-1 of code 0).  Four iterations per tile, fully unrolled so that the code ring needs no moves.
         uint32_t thr_a = ext_a, thr_b = ext_b;
         uint64_t carry = 0ull;
         const uint32_t nblk = (n + 255u) >> 8;
-        for (uint32_t t0 = 0; t0 <= nblk; t0 += kDuoTB) {
-            uint32_t base = t0 * 256u + tid;            // code index of block b = t0 (iteration t0 + 1)
 #define DUO_ITER(CUR, NXT, LOADTO, TB)                                                          \
     {                                                                                           \
         LOADTO = skew_load_code16(lp, base + (TB + 2) * 256u, n);                               \
-        const uint64_t fin = duo_block16(lutb, CUR, NXT, ws2, ws1, bs, loff, keep2, cap2, carry);      \
+        const uint64_t fin = duo_block16(lutb, CUR, NXT, ws2, ws1, bs, loff, keep2, cap2, carry); \
         const uint32_t idx = base + TB * 256u - 256u; /* wraps past 2^32 for the prologue block */ \
         const uint32_t ba = static_cast<uint32_t>(fin), bb = static_cast<uint32_t>(fin >> 32);  \
-        tka.push(idx < n && ba <= thr_a, make_key(ba, idx));                                    \
-        tkb.push(idx < n_b && bb <= thr_b, make_key(bb, idx));                                  \
+        const bool pa = idx < n && ba <= thr_a, pb = idx < n_b && bb <= thr_b;                  \
+        if (__any_sync(0xffffffffu, pa || pb)) { /* rare once a threshold is known */           \
+            tka.push(pa, make_key(ba, idx));                                                    \
+            tkb.push(pb, make_key(bb, idx));                                                    \
+        }                                                                                       \
     }
-#pragma unroll
-            for (int half = 0; half < kDuoTB / 4; half++) {
-                DUO_ITER(c0, c1, c3, 0)
-                DUO_ITER(c1, c2, c0, 1)
-                DUO_ITER(c2, c3, c1, 2)
-                DUO_ITER(c3, c0, c2, 3)
-                base += 1024u;
-            }
-#undef DUO_ITER
+        uint32_t t0 = 0;
+        for (; t0 + (kDuoTB - 1) <= nblk; t0 += kDuoTB) {   // full tiles: iterations t0 .. t0 + 3
+            const uint32_t base = t0 * 256u + tid;          // code index of block b = t0 (iteration t0 + 1)
+            DUO_ITER(c0, c1, c3, 0)
+            DUO_ITER(c1, c2, c0, 1)
+            DUO_ITER(c2, c3, c1, 2)
+            DUO_ITER(c3, c0, c2, 3)
             // one barrier serves both queues; no threshold yet (cold start) -> fold the first tile in right away
             const int lim_a = thr_a == kInfBits ? 0 : kDuoCap - kThreads * kDuoTB;
             const int lim_b = thr_b == kInfBits ? 0 : kDuoCap - kThreads * kDuoTB;
@@ -246,6 +271,13 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
             thr_a = tka.threshold();
             thr_b = tkb.threshold();
         }
+        if (t0 <= nblk) {   // remaining 1..3 iterations (CTA-uniform); the queues have room for a whole tile
+            const uint32_t base = t0 * 256u + tid;
+            DUO_ITER(c0, c1, c3, 0)
+            if (t0 + 1 <= nblk) DUO_ITER(c1, c2, c0, 1)
+            if (t0 + 2 <= nblk) DUO_ITER(c2, c3, c1, 2)
+        }
+#undef DUO_ITER
         __syncthreads();
         tka.flush<kThreads>(ext_a);
         tkb.flush<kThreads>(ext_b);

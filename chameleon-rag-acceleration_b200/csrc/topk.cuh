@@ -103,23 +103,41 @@ struct TopK {
         const int tid = threadIdx.x;
         const int n = meta[1];
         if (n == 0) return;   // uniform
-        int P = 1;
-        while (P < n) P <<= 1;
-        for (int i = n + tid; i < P; i += THREADS) queue[i] = kPadKey;
-        __syncthreads();
-        for (int size = 2; size <= P; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int t = tid; t < (P >> 1); t += THREADS) {
-                    int lo = 2 * t - (t & (stride - 1));
-                    int hi = lo + stride;
-                    bool asc = (lo & size) == 0;
-                    uint64_t a = queue[lo], b = queue[hi];
-                    if ((a > b) == asc) {
-                        queue[lo] = b;
-                        queue[hi] = a;
+        if (n <= 32) {
+            // the common case once a threshold is known: one warp sorts the queue in registers (shuffles only)
+            if (tid < 32) {
+                uint64_t key = tid < n ? queue[tid] : kPadKey;
+#pragma unroll
+                for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        const uint64_t other = __shfl_xor_sync(0xffffffffu, key, stride);
+                        const bool keep_min = ((tid & stride) == 0) == ((tid & size) == 0);
+                        key = ((key < other) == keep_min) ? key : other;
                     }
                 }
-                __syncthreads();
+                queue[tid] = key;
+            }
+            __syncthreads();
+        } else {
+            int P = 1;
+            while (P < n) P <<= 1;
+            for (int i = n + tid; i < P; i += THREADS) queue[i] = kPadKey;
+            __syncthreads();
+            for (int size = 2; size <= P; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = tid; t < (P >> 1); t += THREADS) {
+                        int lo = 2 * t - (t & (stride - 1));
+                        int hi = lo + stride;
+                        bool asc = (lo & size) == 0;
+                        uint64_t a = queue[lo], b = queue[hi];
+                        if ((a > b) == asc) {
+                            queue[lo] = b;
+                            queue[hi] = a;
+                        }
+                    }
+                    __syncthreads();
+                }
             }
         }
         const int cur = meta[2], nb = meta[0];
