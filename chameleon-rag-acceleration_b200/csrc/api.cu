@@ -99,10 +99,11 @@ struct b200_ivfpq_index {
     DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t;
     DevBuf host_xq, host_D, host_I;
     // tensor-core coarse quantizer (K1): split-bf16 centroids, norms, per-call buffers
-    DevBuf cent_bf16, cnorm, cmax2, q_bf16, qnorm, cand, cand_score, flags, nflagged;
+    DevBuf cent_bf16, cnorm, cmax2, q_bf16, qnorm, cand, cand_score, cand_cnt, flags, nflagged;
     CUtensorMap tmB;
     bool tc_ready = false;
-    int coarse_variant = 0;   // 0 = auto (tensor cores when possible), 1 = exact kernels only
+    int coarse_variant = 0;   // 0 = auto (tensor cores when possible), 1 = exact kernels only, 2 = tensor cores with the
+                              // full score matrix + radix select (no two-pass filter)
     int kpad = 0;
     // instrumentation
     bool timing = false;
@@ -170,60 +171,99 @@ bool tc_usable(const b200_ivfpq_index* h, int nprobe) {
     return tc_candidates(h, nprobe) < h->nlist;   // otherwise every centroid would be a candidate anyway
 }
 
-// approximate scores s(q, c) = ||c||^2 - 2 q.c for one chunk of queries, on the tensor cores
-int run_tc_scores(b200_ivfpq_index* h, int64_t nq, const float* d_xq, float* d_scores, cudaStream_t st) {
+// one pass of the tensor-core GEMM over a chunk of queries (split-bf16 operand prepared by tc_prepare_queries)
+template <int MODE>
+int launch_tc_gemm(b200_ivfpq_index* h, int64_t nq, TcGemmParams gp, cudaStream_t st) {
+    CUtensorMap tmA;
+    if (!tc_make_map(&tmA, h->q_bf16.p, nq, h->kpad, kTcBM))
+        return fail(B200_IVFPQ_ECUDA, "cuTensorMapEncodeTiled failed for the query operand");
+    gp.cnorm = h->cnorm.as<float>();
+    gp.qnorm = h->qnorm.as<float>();
+    gp.nq = nq;
+    gp.nlist = h->nlist;
+    gp.kblocks = h->kpad / kTcBK;
+    gp.mtiles = (int)((nq + kTcBM - 1) / kTcBM);
+    gp.ntiles = (int)((h->nlist + kTcBN - 1) / kTcBN);
+    CUDA_TRY(cudaFuncSetAttribute(coarse_tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kTcSmemBytes));
+    int grid = std::min<int64_t>((int64_t)gp.mtiles * gp.ntiles, h->num_sms);
+    coarse_tc_gemm_kernel<MODE><<<grid, kTcThreads, kTcSmemBytes, st>>>(tmA, h->tmB, gp);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int tc_prepare_queries(b200_ivfpq_index* h, int64_t nq, const float* d_xq, cudaStream_t st) {
     int rc;
     if ((rc = h->q_bf16.ensure(sizeof(__nv_bfloat16) * nq * h->kpad))) return rc;
     if ((rc = h->qnorm.ensure(sizeof(float) * nq))) return rc;
     tc_split_rows_kernel<<<(unsigned)nq, 128, 0, st>>>(d_xq, nq, h->d, h->kpad, 1, h->q_bf16.as<__nv_bfloat16>(),
                                                       h->qnorm.as<float>());
     LAUNCH_CHECK();
-    CUtensorMap tmA;
-    if (!tc_make_map(&tmA, h->q_bf16.p, nq, h->kpad, kTcBM))
-        return fail(B200_IVFPQ_ECUDA, "cuTensorMapEncodeTiled failed for the query operand");
-    TcGemmParams gp;
-    gp.cnorm = h->cnorm.as<float>();
-    gp.qnorm = h->qnorm.as<float>();
-    gp.out = d_scores;
-    gp.nq = nq;
-    gp.nlist = h->nlist;
-    gp.kblocks = h->kpad / kTcBK;
-    gp.mtiles = (int)((nq + kTcBM - 1) / kTcBM);
-    gp.ntiles = (int)((h->nlist + kTcBN - 1) / kTcBN);
-    CUDA_TRY(cudaFuncSetAttribute(coarse_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kTcSmemBytes));
-    int grid = std::min<int64_t>((int64_t)gp.mtiles * gp.ntiles, h->num_sms);
-    coarse_tc_gemm_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tmA, h->tmB, gp);
-    LAUNCH_CHECK();
     return 0;
+}
+
+// approximate scores s(q, c) = ||c||^2 - 2 q.c for one chunk of queries, on the tensor cores
+int run_tc_scores(b200_ivfpq_index* h, int64_t nq, const float* d_xq, float* d_scores, cudaStream_t st) {
+    int rc;
+    if ((rc = tc_prepare_queries(h, nq, d_xq, st))) return rc;
+    TcGemmParams gp{};
+    gp.out = d_scores;
+    return launch_tc_gemm<kTcScores>(h, nq, gp, st);
 }
 
 // K1 for one chunk of queries: distances to all centroids, then nprobe-select.
 int run_coarse(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int nprobe, int32_t* probe32, int64_t* ids64,
                float* dis, cudaStream_t st, bool time_stages) {
-    int rc = h->coarse_mat.ensure(sizeof(float) * nq * h->nlist);
-    if (rc) return rc;
+    int rc;
     if (tc_usable(h, nprobe)) {
         // tensor-core pre-filter + exact rescoring (coarse_tc.cuh)
         const int L = tc_candidates(h, nprobe);
-        if ((rc = h->cand.ensure(sizeof(int32_t) * nq * L))) return rc;
+        const int64_t nchunks = (h->nlist + 31) / 32;
+        const bool two_pass = nchunks >= L && h->coarse_variant != 2;
+        const int cap = two_pass ? std::min(4 * L, 2048) : L;
+        if ((rc = h->cand.ensure(sizeof(int32_t) * nq * std::max(cap, L)))) return rc;
         if ((rc = h->cand_score.ensure(sizeof(float) * nq * L))) return rc;
         if ((rc = h->flags.ensure(sizeof(int) * nq))) return rc;
         if (!h->nflagged.p) {
             if ((rc = h->nflagged.ensure(sizeof(int)))) return rc;
             CUDA_TRY(cudaMemsetAsync(h->nflagged.p, 0, sizeof(int), st));
         }
-        if ((rc = run_tc_scores(h, nq, d_xq, h->coarse_mat.as<float>(), st))) return rc;
-        if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
-        if ((rc = launch_select(h, h->coarse_mat.as<float>(), nq, h->nlist, L, h->cand.as<int32_t>(), nullptr,
-                                h->cand_score.as<float>(), st)))
-            return rc;
+        const int* cand_cnt = nullptr;
+        if (two_pass) {
+            // no (nq, nlist) matrix: chunk minima -> tau = L-th smallest minimum -> the same GEMM again as a filter
+            if ((rc = h->coarse_mat.ensure(sizeof(float) * nq * nchunks))) return rc;
+            if ((rc = h->cand_cnt.ensure(sizeof(int) * nq))) return rc;
+            if ((rc = tc_prepare_queries(h, nq, d_xq, st))) return rc;
+            TcGemmParams gp{};
+            gp.out = h->coarse_mat.as<float>();
+            gp.nchunks = nchunks;
+            if ((rc = launch_tc_gemm<kTcMinima>(h, nq, gp, st))) return rc;
+            if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+            if ((rc = launch_select(h, h->coarse_mat.as<float>(), nq, nchunks, L, h->cand.as<int32_t>(), nullptr,
+                                    h->cand_score.as<float>(), st)))
+                return rc;
+            CUDA_TRY(cudaMemsetAsync(h->cand_cnt.p, 0, sizeof(int) * nq, st));
+            gp.tau = h->cand_score.as<float>() + (L - 1);
+            gp.tau_stride = L;
+            gp.cand = h->cand.as<int32_t>();
+            gp.cand_cnt = h->cand_cnt.as<int>();
+            gp.cap = cap;
+            if ((rc = launch_tc_gemm<kTcFilter>(h, nq, gp, st))) return rc;
+            cand_cnt = h->cand_cnt.as<int>();
+        } else {
+            if ((rc = h->coarse_mat.ensure(sizeof(float) * nq * h->nlist))) return rc;
+            if ((rc = run_tc_scores(h, nq, d_xq, h->coarse_mat.as<float>(), st))) return rc;
+            if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+            if ((rc = launch_select(h, h->coarse_mat.as<float>(), nq, h->nlist, L, h->cand.as<int32_t>(), nullptr,
+                                    h->cand_score.as<float>(), st)))
+                return rc;
+        }
         const float eps_rel = 6e-5f, eps_abs = (float)(h->d + 2) * 1.1920929e-7f;
-        size_t rsm = sizeof(float) * ((h->d + 3) & ~3) + TopK::smem_bytes(nprobe, 2048);
+        size_t rsm = rescore_smem_bytes(h->d, nprobe);
         if ((rc = set_smem(coarse_rescore_kernel, rsm))) return rc;
         coarse_rescore_kernel<<<(unsigned)nq, kRescoreThreads, rsm, st>>>(
-            d_xq, h->cent, h->qnorm.as<float>(), h->cmax2.as<float>(), h->cand.as<int32_t>(),
-            h->cand_score.as<float>(), L, h->d, h->nlist, nprobe, eps_rel, eps_abs, probe32, ids64, dis,
+            d_xq, h->cent, h->qnorm.as<float>(), h->cmax2.as<float>(), h->cand.as<int32_t>(), cand_cnt, cap,
+            h->cand_score.as<float>() + (L - 1), L, h->d, h->nlist, nprobe, eps_rel, eps_abs, probe32, ids64, dis,
             h->flags.as<int>());
         LAUNCH_CHECK();
         size_t fsm = sizeof(float) * ((h->d + 3) & ~3) + TopK::smem_bytes(nprobe, kSelCap);
@@ -234,6 +274,7 @@ int run_coarse(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int nprobe, i
         LAUNCH_CHECK();
         return 0;
     }
+    if ((rc = h->coarse_mat.ensure(sizeof(float) * nq * h->nlist))) return rc;
     dim3 grid(static_cast<unsigned>((h->nlist + kCoarseTile - 1) / kCoarseTile),
               static_cast<unsigned>((nq + kCoarseTile - 1) / kCoarseTile));
     coarse_dist_kernel<<<grid, kThreads, 0, st>>>(d_xq, h->cent, h->coarse_mat.as<float>(), (int)nq, h->nlist, h->d,
@@ -462,7 +503,7 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     v = getenv("B200_IVFPQ_NSEG");
     if (v) h->force_nseg = std::max(0, std::min(16, atoi(v)));
     v = getenv("B200_IVFPQ_COARSE");
-    if (v) h->coarse_variant = !strcmp(v, "exact") ? 1 : 0;
+    if (v) h->coarse_variant = !strcmp(v, "exact") ? 1 : !strcmp(v, "matrix") ? 2 : 0;
     *out = h;
     return 0;
 }
@@ -473,7 +514,7 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
     DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t, &h->gstart, &h->groups,
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
                       &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
-                      &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged};
+                      &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged, &h->cand_cnt};
     for (DevBuf* b : bufs) b->release();
     for (auto& set : h->evs)
         for (auto& e : set)

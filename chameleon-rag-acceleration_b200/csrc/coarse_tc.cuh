@@ -143,13 +143,34 @@ __device__ __forceinline__ constexpr uint32_t tc_idesc() {
 struct TcGemmParams {
     const float* cnorm;   // (nlist)
     const float* qnorm;   // (nq)
-    float* out;           // (nq, nlist) scores: max(0, qnorm[q] + cnorm[c] - 2 q.c)  (approximate L2^2, >= 0 so
-                          // that the unsigned-key top-k orders them; clamping only moves towards the truth)
+    float* out;           // kTcScores: (nq, nlist) scores max(0, qnorm[q] + cnorm[c] - 2 q.c)  (approximate L2^2, >= 0
+                          // so that the unsigned-key top-k orders them; clamping only moves towards the truth)
+                          // kTcMinima: (nq, nchunks) minimum score of every 32-centroid chunk
     int64_t nq, nlist;
     int kblocks;          // kpad / 64
     int mtiles, ntiles;
+    // kTcFilter: every centroid with score <= tau[q * tau_stride] is appended to cand[q * cap ..] (cand_cnt[q] counts
+    // ALL of them, also those beyond cap)
+    int64_t nchunks;
+    const float* tau;
+    int tau_stride;
+    int32_t* cand;
+    int* cand_cnt;
+    int cap;
 };
 
+// The epilogue never needs the (nq, nlist) score matrix in HBM when the candidates are selected in two passes of the
+// same deterministic GEMM:
+//   pass 1 (kTcMinima)  minimum score of every 32-centroid chunk, (nq, nlist / 32);  the L-th smallest chunk minimum
+//                       tau is an upper bound of the L-th smallest score (L chunks hold a score <= tau);
+//   pass 2 (kTcFilter)  the same GEMM again; centroids with score <= tau are the candidates (at least L of them, a few
+//                       more in expectation), every non-candidate has score > tau -- which is what the sufficiency
+//                       proof of coarse_rescore_kernel needs.
+// Recomputing 2 nq nlist 3d flops on the tensor cores is far cheaper than writing and re-reading the matrix
+// (C3: 2.6 GB per 10k queries).
+enum TcMode { kTcScores = 0, kTcMinima = 1, kTcFilter = 2 };
+
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 coarse_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const TcGemmParams p) {
@@ -262,8 +283,13 @@ coarse_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc_fence_after();
             const int64_t row = static_cast<int64_t>(m_blk) * kTcBM + ew * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * kTcBN);
-            float* orow = p.out + row * p.nlist;
+            float* orow = p.out + row * (MODE == kTcMinima ? p.nchunks : p.nlist);
             const float qn = row < p.nq ? __ldg(p.qnorm + row) : 0.0f;
+            float tau = 0.0f;
+            if (MODE == kTcFilter && row < p.nq) tau = __ldg(p.tau + row * p.tau_stride);
+            uint32_t hit[kTcBN / 32];   // kTcFilter: bit j of hit[i] = column 32 i + j of this tile is a candidate
+#pragma unroll
+            for (int i = 0; i < kTcBN / 32; i++) hit[i] = 0u;
 #pragma unroll 1
             for (int c0 = 0; c0 < kTcBN; c0 += 32) {
                 uint32_t v[32];
@@ -279,24 +305,62 @@ coarse_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     : "r"(taddr + static_cast<uint32_t>(c0)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int64_t cbase = static_cast<int64_t>(n_blk) * kTcBN + c0;
-                if (row < p.nq) {
-                    if (cbase + 32 <= p.nlist && (p.nlist & 3) == 0) {
+                if (row < p.nq && cbase < p.nlist) {
+                    const bool full = cbase + 32 <= p.nlist && (p.nlist & 3) == 0;
+                    if (MODE == kTcScores) {
+                        if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 cn = __ldg(reinterpret_cast<const float4*>(p.cnorm + cbase + j));
-                            float4 o;
-                            o.x = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 0]), cn.x + qn));
-                            o.y = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 1]), cn.y + qn));
-                            o.z = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 2]), cn.z + qn));
-                            o.w = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 3]), cn.w + qn));
-                            *reinterpret_cast<float4*>(orow + cbase + j) = o;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 cn = __ldg(reinterpret_cast<const float4*>(p.cnorm + cbase + j));
+                                float4 o;
+                                o.x = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 0]), cn.x + qn));
+                                o.y = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 1]), cn.y + qn));
+                                o.z = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 2]), cn.z + qn));
+                                o.w = fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j + 3]), cn.w + qn));
+                                *reinterpret_cast<float4*>(orow + cbase + j) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (cbase + j < p.nlist)
+                                    orow[cbase + j] = fmaxf(
+                                        0.0f, fmaf(-2.0f, __uint_as_float(v[j]), __ldg(p.cnorm + cbase + j) + qn));
                         }
                     } else {
+                        // unclamped scores of the chunk (same expression as above, so the three modes agree bit for
+                        // bit); columns past nlist count as +inf
+                        float sc[32];
+                        if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if (cbase + j < p.nlist)
-                                orow[cbase + j] =
-                                    fmaxf(0.0f, fmaf(-2.0f, __uint_as_float(v[j]), __ldg(p.cnorm + cbase + j) + qn));
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 cn = __ldg(reinterpret_cast<const float4*>(p.cnorm + cbase + j));
+                                sc[j + 0] = fmaf(-2.0f, __uint_as_float(v[j + 0]), cn.x + qn);
+                                sc[j + 1] = fmaf(-2.0f, __uint_as_float(v[j + 1]), cn.y + qn);
+                                sc[j + 2] = fmaf(-2.0f, __uint_as_float(v[j + 2]), cn.z + qn);
+                                sc[j + 3] = fmaf(-2.0f, __uint_as_float(v[j + 3]), cn.w + qn);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                sc[j] = cbase + j < p.nlist
+                                            ? fmaf(-2.0f, __uint_as_float(v[j]), __ldg(p.cnorm + cbase + j) + qn)
+                                            : __uint_as_float(kInfBits);
+                        }
+                        float mn = sc[0];
+#pragma unroll
+                        for (int j = 1; j < 32; j++) mn = fminf(mn, sc[j]);
+                        mn = fmaxf(0.0f, mn);
+                        if (MODE == kTcMinima) {
+                            orow[cbase >> 5] = mn;
+                        } else {
+                            // clamping commutes with the comparison (tau >= 0)
+                            uint32_t m = 0u;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) m |= (sc[j] <= tau ? 1u : 0u) << j;
+#pragma unroll
+                            for (int i = 0; i < kTcBN / 32; i++)
+                                if (i == c0 / 32) hit[i] = m;
+                        }
                     }
                 }
             }
@@ -305,6 +369,28 @@ coarse_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (++as == 2) {
                 as = 0;
                 aphase ^= 1u;
+            }
+            if (MODE == kTcFilter) {
+                // the accumulator stage is already released; one returning atomic per row and tile (its latency would
+                // otherwise be paid per candidate)
+                int total = 0;
+#pragma unroll
+                for (int i = 0; i < kTcBN / 32; i++) total += __popc(hit[i]);
+                if (total > 0) {
+                    int pos = atomicAdd(p.cand_cnt + row, total);
+#pragma unroll
+                    for (int i = 0; i < kTcBN / 32; i++) {
+                        uint32_t m = hit[i];
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            if (pos < p.cap)
+                                p.cand[row * p.cap + pos] =
+                                    static_cast<int32_t>(static_cast<int64_t>(n_blk) * kTcBN + 32 * i + j);
+                            pos++;
+                        }
+                    }
+                }
             }
         }
     }
@@ -317,45 +403,89 @@ coarse_tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // ---- exact rescoring of the candidates + proof of sufficiency ---------------------------------------------------
-// One CTA per query.  cand: (nq, L) centroid ids sorted by approximate score (ascending), cand_score the scores.
-// Writes the nprobe smallest (exact distance, id) and flags the query when the candidates cannot be proven
-// sufficient.  eps_rel * ||q|| * cmax + eps_abs * (||q|| + cmax)^2 bounds |approximate - oracle| distance.
+// One CTA per query.  cand: (nq, cap) centroid ids; the first min(cand_cnt[q], cap) are valid (cand_cnt == nullptr:
+// all cap).  bound[q * bound_stride] is a score every NON-candidate is known to reach or exceed: the L-th smallest
+// approximate score (radix-select path) or the filter threshold tau (two-pass path).  Writes the nprobe smallest
+// (exact distance, id) and flags the query when the candidates cannot be proven sufficient (or overflowed cap).
+// eps_rel * ||q|| * cmax + eps_abs * (||q|| + cmax)^2 bounds |approximate - oracle| distance.
 constexpr int kRescoreThreads = 128;
+constexpr int kRescoreJ = 32;                       // dimensions staged per step
+constexpr int kRescoreTileWords = kRescoreThreads * (kRescoreJ + 1);
+
+__host__ __device__ inline size_t rescore_smem_bytes(int d, int nprobe) {
+    return sizeof(float) * (static_cast<size_t>((d + 3) & ~3) + kRescoreTileWords) + TopK::smem_bytes(nprobe, 2048) +
+           sizeof(int) * kRescoreThreads;
+}
 
 __global__ void __launch_bounds__(kRescoreThreads)
 coarse_rescore_kernel(const float* __restrict__ xq, const float* __restrict__ cent, const float* __restrict__ qnorm,
                       const float* __restrict__ cmax2, const int32_t* __restrict__ cand,
-                      const float* __restrict__ cand_score, int L, int d, int64_t nlist, int nprobe, float eps_rel,
-                      float eps_abs, int32_t* __restrict__ probe32, int64_t* __restrict__ ids64,
-                      float* __restrict__ dis_out, int* __restrict__ flags) {
+                      const int* __restrict__ cand_cnt, int cap, const float* __restrict__ bound, int bound_stride,
+                      int d, int64_t nlist, int nprobe, float eps_rel, float eps_abs, int32_t* __restrict__ probe32,
+                      int64_t* __restrict__ ids64, float* __restrict__ dis_out, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sq = reinterpret_cast<float*>(smem_raw);                 // query, d floats
+    float* tile = sq + ((d + 3) & ~3);                              // [128 candidates][32 + 1] staged centroid slices
     TopK tk;
-    tk.bind(sq + ((d + 3) & ~3), nprobe, 2048);
-    const int tid = threadIdx.x;
+    tk.bind(tile + kRescoreTileWords, nprobe, 2048);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
+    const int found = cand_cnt ? cand_cnt[q] : cap;
+    const int L = found < cap ? found : cap;
     for (int j = tid; j < d; j += kRescoreThreads) sq[j] = xq[q * d + j];
     if (tid == 0) tk.reset(kInfBits);
     __syncthreads();
     uint32_t thr = kInfBits;
-    for (int base = 0; base < L; base += kRescoreThreads * 4) {
-#pragma unroll 1
-        for (int u = 0; u < 4; u++) {
-            const int i = base + u * kRescoreThreads + tid;
-            uint32_t bits = 0xffffffffu;
-            int32_t id = -1;
-            if (i < L) {
-                id = cand[q * L + i];
-                if (id >= 0) {
-                    const float* c = cent + static_cast<int64_t>(id) * d;
-                    float acc = 0.0f;
-                    for (int j = 0; j < d; j++) acc = sqdiff_acc(acc, sq[j], __ldg(c + j));
-                    bits = __float_as_uint(acc);
+    // 128 candidates at a time, one per thread.  Each thread must add its candidate's d terms in order, so the rows
+    // are staged through shared memory in 32-dimension slices: the warps read them from global memory coalesced
+    // (lane = dimension) and every thread then walks its own row (stride 33 words: conflict-free).
+    int* s_ids = reinterpret_cast<int*>(tk.meta + 4);               // [128] candidate ids of the current batch
+    const bool vec4 = (d & 3) == 0;
+    for (int base = 0; base < L; base += kRescoreThreads) {
+        const int nc = min(kRescoreThreads, L - base);
+        const int32_t my_id = tid < nc ? cand[q * cap + base + tid] : -1;
+        s_ids[tid] = my_id;
+        __syncthreads();
+        float acc = 0.0f;
+        for (int j0 = 0; j0 < d; j0 += kRescoreJ) {
+            const int jn = min(kRescoreJ, d - j0);
+            if (vec4) {
+                // 8 threads x float4 cover one 128-byte row slice, 16 rows per pass; all loads of a slice in flight
+                const int c4 = (tid & 7) * 4, r0 = tid >> 3;
+                float4 v[kRescoreThreads / 16];
+#pragma unroll
+                for (int ps = 0; ps < kRescoreThreads / 16; ps++) {
+                    const int i = r0 + 16 * ps;
+                    const int32_t id = i < nc ? s_ids[i] : -1;
+                    v[ps] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (id >= 0 && c4 < jn)
+                        v[ps] = __ldg(reinterpret_cast<const float4*>(cent + static_cast<int64_t>(id) * d + j0 + c4));
+                }
+#pragma unroll
+                for (int ps = 0; ps < kRescoreThreads / 16; ps++) {
+                    float* t = tile + (r0 + 16 * ps) * (kRescoreJ + 1) + c4;
+                    t[0] = v[ps].x;
+                    t[1] = v[ps].y;
+                    t[2] = v[ps].z;
+                    t[3] = v[ps].w;
+                }
+            } else {
+                for (int i = warp; i < nc; i += kRescoreThreads / 32) {
+                    const int32_t id = s_ids[i];
+                    if (lane < jn && id >= 0)
+                        tile[i * (kRescoreJ + 1) + lane] = __ldg(cent + static_cast<int64_t>(id) * d + j0 + lane);
                 }
             }
-            tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(id)));
+            __syncthreads();
+            if (my_id >= 0) {
+                const float* row = tile + tid * (kRescoreJ + 1);
+                for (int jj = 0; jj < jn; jj++) acc = sqdiff_acc(acc, sq[j0 + jj], row[jj]);
+            }
+            __syncthreads();
         }
-        tk.sync_and_flush_if_over<kRescoreThreads>(2048 - kRescoreThreads * 4, kInfBits);
+        const uint32_t bits = my_id >= 0 ? __float_as_uint(acc) : 0xffffffffu;
+        tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(my_id)));
+        tk.sync_and_flush_if_over<kRescoreThreads>(2048 - kRescoreThreads, kInfBits);
         thr = tk.threshold();
     }
     __syncthreads();
@@ -374,10 +504,10 @@ coarse_rescore_kernel(const float* __restrict__ xq, const float* __restrict__ ce
         if (dis_out) dis_out[q * nprobe + i] = dv;
     }
     if (tid == 0) {
-        int flag = 0;
-        if (L < nlist) {
-            // worst (largest) approximate score among the candidates bounds every non-candidate from below
-            const float sL = cand_score[q * L + (L - 1)];
+        int flag = found > cap ? 1 : 0;
+        if (found < nlist) {
+            // every non-candidate has an approximate score >= sL
+            const float sL = bound[q * bound_stride];
             const float qn = qnorm[q];
             const float a = sqrtf(qn), b = sqrtf(*cmax2);
             const float E = eps_rel * a * b + eps_abs * (a + b) * (a + b);

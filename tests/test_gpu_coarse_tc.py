@@ -45,14 +45,17 @@ def test_tc_scores_match_fp64(nq, nlist, d):
 
 
 @pytest.mark.parametrize("d,nlist,nq,nprobe", [(128, 1024, 500, 16), (96, 700, 129, 64), (128, 8192, 300, 32),
-                                              (768, 600, 40, 32), (64, 300, 50, 1)])
+                                              (768, 600, 40, 32), (64, 300, 50, 1),
+                                              (128, 3001, 100, 8),       # two-pass filter, ragged last chunk
+                                              (96, 65536, 150, 64),      # C3's coarse quantizer: two-pass, L = 128
+                                              (32, 4096, 700, 5)])
 def test_tc_coarse_identical_to_oracle(oracle, d, nlist, nq, nprobe):
     import b200ivfpq as faiss
     rng = np.random.default_rng(d + nlist)
     cent = rng.random((nlist, d), dtype=np.float32)
     xq = (cent[rng.integers(0, nlist, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 0.2).astype(np.float32)
     dr, ir = oracle.C.coarse(xq, cent, nprobe)
-    for variant in ("auto", "exact"):
+    for variant in ("auto", "matrix", "exact"):   # two-pass filter when nlist / 32 >= L, score matrix + select, fp32
         os.environ["B200_IVFPQ_COARSE"] = variant
         try:
             idx = faiss.IndexFlatL2(d)
@@ -62,7 +65,7 @@ def test_tc_coarse_identical_to_oracle(oracle, d, nlist, nq, nprobe):
             del os.environ["B200_IVFPQ_COARSE"]
         _util.assert_bit_equal(I, ir, f"probed ids ({variant})")
         _util.assert_bit_equal(D, dr, f"coarse distances ({variant})")
-        if variant == "auto":
+        if variant != "exact":
             from b200ivfpq import _lib
             h = idx._ensure_handle()
             n = ctypes.c_int64()
@@ -70,13 +73,14 @@ def test_tc_coarse_identical_to_oracle(oracle, d, nlist, nq, nprobe):
             assert n.value <= max(1, nq // 50), f"{n.value} of {nq} queries fell back to the exact kernel"
 
 
-def test_tc_coarse_adversarial_near_ties(oracle):
+@pytest.mark.parametrize("nlist", [600, 2400])   # 2400: two-pass filter, the duplicates overflow its candidate cap
+def test_tc_coarse_adversarial_near_ties(oracle, nlist):
     """Centroids that differ by less than the GEMM's error: the proof must fail and the exact fallback must
     restore the oracle's answer (ties -> lower id)."""
     import b200ivfpq as faiss
     from b200ivfpq import _lib
     rng = np.random.default_rng(0)
-    d, nlist, nq, nprobe = 128, 600, 64, 8
+    d, nq, nprobe = 128, 64, 8
     base = rng.random((6, d), dtype=np.float32)
     cent = base[rng.integers(0, 6, nlist)].copy()
     cent += (rng.standard_normal((nlist, d)) * 1e-6).astype(np.float32)      # 100 near-duplicates per base
