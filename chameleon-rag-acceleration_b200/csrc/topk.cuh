@@ -96,6 +96,35 @@ struct TopK {
         return lo;
     }
 
+    // ---- warp-level sorting networks over one 64-bit key per lane (shuffles only) ----
+    // bitonic sequence across the lanes -> ascending
+    static __device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t key, int lane) {
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, key, stride);
+            const bool keep_min = (lane & stride) == 0;
+            key = ((key < other) == keep_min) ? key : other;
+        }
+        return key;
+    }
+    static __device__ __forceinline__ uint64_t warp_sort32(uint64_t key, int lane) {
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const uint64_t other = __shfl_xor_sync(0xffffffffu, key, stride);
+                const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
+                key = ((key < other) == keep_min) ? key : other;
+            }
+        }
+        return key;
+    }
+    // a, b ascending across the lanes -> the 32 smallest of their union, ascending
+    static __device__ __forceinline__ uint64_t warp_lower32(uint64_t a, uint64_t b, int lane) {
+        const uint64_t brev = __shfl_sync(0xffffffffu, b, 31 - lane);
+        return warp_bitonic_merge32(a < brev ? a : brev, lane);
+    }
+
     // all THREADS threads call, after a __syncthreads() that made the queue writes visible.
     // ext_thr: an externally known upper bound on the k-th best distance (kInfBits if none).
     template <int THREADS>
@@ -106,17 +135,28 @@ struct TopK {
         if (n <= 32) {
             // the common case once a threshold is known: one warp sorts the queue in registers (shuffles only)
             if (tid < 32) {
-                uint64_t key = tid < n ? queue[tid] : kPadKey;
-#pragma unroll
-                for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                        const uint64_t other = __shfl_xor_sync(0xffffffffu, key, stride);
-                        const bool keep_min = ((tid & stride) == 0) == ((tid & size) == 0);
-                        key = ((key < other) == keep_min) ? key : other;
-                    }
-                }
+                const uint64_t key = warp_sort32(tid < n ? queue[tid] : kPadKey, tid);
                 queue[tid] = key;
+            }
+            __syncthreads();
+        } else if (k <= 32) {
+            // only the 32 smallest can matter: every warp reduces its share of the queue to a sorted run of its 32
+            // smallest in registers (sort 32, then "merge and keep the lower half"), warp 0 merges the runs.
+            // Three barriers instead of one per stage of a shared-memory bitonic sort of the whole queue.
+            const int lane = tid & 31, w = tid >> 5;
+            uint64_t acc = kPadKey;
+            for (int base = w * 32; base < n; base += THREADS) {
+                const int i = base + lane;
+                const uint64_t key = warp_sort32(i < n ? queue[i] : kPadKey, lane);
+                acc = warp_lower32(acc, key, lane);
+            }
+            __syncthreads();
+            queue[tid] = acc;
+            __syncthreads();
+            if (w == 0) {
+                uint64_t a = queue[lane];
+                for (int j = 1; j < THREADS / 32; j++) a = warp_lower32(a, queue[j * 32 + lane], lane);
+                queue[lane] = a;
             }
             __syncthreads();
         } else {
