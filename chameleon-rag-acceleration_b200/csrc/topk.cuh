@@ -96,33 +96,94 @@ struct TopK {
         return lo;
     }
 
-    // ---- warp-level sorting networks over one 64-bit key per lane (shuffles only) ----
-    // bitonic sequence across the lanes -> ascending
-    static __device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t key, int lane) {
-#pragma unroll
-        for (int stride = 16; stride > 0; stride >>= 1) {
-            const uint64_t other = __shfl_xor_sync(0xffffffffu, key, stride);
-            const bool keep_min = (lane & stride) == 0;
-            key = ((key < other) == keep_min) ? key : other;
-        }
-        return key;
+    // ---- warp-level sorting networks (registers + shuffles only) -----------------------------------------------
+    // A run of 32 R keys lives in one warp: element e = 32 r + lane is v[r] of that lane.  Compare-exchanges with
+    // stride >= 32 are register-to-register, smaller strides are butterfly shuffles.
+    static __device__ __forceinline__ void cmpx(uint64_t& lo, uint64_t& hi, bool asc) {
+        const bool sw = (lo > hi) == asc;
+        const uint64_t a = sw ? hi : lo, b = sw ? lo : hi;
+        lo = a;
+        hi = b;
     }
-    static __device__ __forceinline__ uint64_t warp_sort32(uint64_t key, int lane) {
+    template <int R>
+    static __device__ __forceinline__ void warp_stage(uint64_t (&v)[R], int lane, int size, int stride) {
+        if (stride >= 32) {
+            const int rs = stride >> 5;
 #pragma unroll
-        for (int size = 2; size <= 32; size <<= 1) {
+            for (int r = 0; r < R; r++)
+                if ((r & rs) == 0) cmpx(v[r], v[r + rs], ((r << 5) & size) == 0);
+        } else {
 #pragma unroll
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                const uint64_t other = __shfl_xor_sync(0xffffffffu, key, stride);
-                const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
-                key = ((key < other) == keep_min) ? key : other;
+            for (int r = 0; r < R; r++) {
+                const uint64_t other = __shfl_xor_sync(0xffffffffu, v[r], stride);
+                const bool asc = ((((r << 5) | lane) & size) == 0);
+                const bool keep_min = ((lane & stride) == 0) == asc;
+                v[r] = ((v[r] < other) == keep_min) ? v[r] : other;
             }
         }
-        return key;
     }
-    // a, b ascending across the lanes -> the 32 smallest of their union, ascending
-    static __device__ __forceinline__ uint64_t warp_lower32(uint64_t a, uint64_t b, int lane) {
-        const uint64_t brev = __shfl_sync(0xffffffffu, b, 31 - lane);
-        return warp_bitonic_merge32(a < brev ? a : brev, lane);
+    template <int R>
+    static __device__ __forceinline__ void warp_sort(uint64_t (&v)[R], int lane) {
+#pragma unroll
+        for (int size = 2; size <= 32 * R; size <<= 1)
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) warp_stage<R>(v, lane, size, stride);
+    }
+    // a, b ascending runs -> a = the 32 R smallest of their union, ascending
+    template <int R>
+    static __device__ __forceinline__ void warp_lower(uint64_t (&a)[R], const uint64_t (&b)[R], int lane) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint64_t brev = __shfl_sync(0xffffffffu, b[R - 1 - r], 31 - lane);
+            a[r] = a[r] < brev ? a[r] : brev;
+        }
+#pragma unroll
+        for (int stride = 16 * R; stride > 0; stride >>= 1) warp_stage<R>(a, lane, 64 * R, stride);   // all ascending
+    }
+    static __device__ __forceinline__ uint64_t warp_sort32(uint64_t key, int lane) {
+        uint64_t v[1] = {key};
+        warp_sort<1>(v, lane);
+        return v[0];
+    }
+
+    // n > 32 R queue entries -> queue[0 .. 32 R) = their 32 R smallest, ascending.  Every warp reduces its share of
+    // the queue to one sorted run in registers ("sort a chunk, merge, keep the lower half"), warp 0 merges the runs:
+    // three barriers instead of one per stage of a shared-memory bitonic sort of the whole queue.
+    // (a free-standing function, not inlined: the sorting networks are large and run rarely compared with the scan
+    // loops they would otherwise be inlined into several times)
+    template <int R, int THREADS>
+    static __device__ __noinline__ void reduce_queue(uint64_t* __restrict__ queue, int n) {
+        constexpr int NW = THREADS / 32, RUN = 32 * R;
+        const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+        uint64_t acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = kPadKey;
+        for (int base = w * RUN; base < n; base += NW * RUN) {
+            uint64_t v[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = base + 32 * r + lane;
+                v[r] = i < n ? queue[i] : kPadKey;
+            }
+            warp_sort<R>(v, lane);
+            warp_lower<R>(acc, v, lane);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; r++) queue[w * RUN + 32 * r + lane] = acc[r];
+        __syncthreads();
+        if (w == 0) {
+            const int nruns = min(NW, (n + RUN - 1) / RUN);   // warps beyond that hold only padding
+            for (int j = 1; j < nruns; j++) {
+                uint64_t v[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) v[r] = queue[j * RUN + 32 * r + lane];
+                warp_lower<R>(acc, v, lane);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) queue[32 * r + lane] = acc[r];
+        }
+        __syncthreads();
     }
 
     // all THREADS threads call, after a __syncthreads() that made the queue writes visible.
@@ -139,26 +200,12 @@ struct TopK {
                 queue[tid] = key;
             }
             __syncthreads();
-        } else if (k <= 32) {
-            // only the 32 smallest can matter: every warp reduces its share of the queue to a sorted run of its 32
-            // smallest in registers (sort 32, then "merge and keep the lower half"), warp 0 merges the runs.
-            // Three barriers instead of one per stage of a shared-memory bitonic sort of the whole queue.
-            const int lane = tid & 31, w = tid >> 5;
-            uint64_t acc = kPadKey;
-            for (int base = w * 32; base < n; base += THREADS) {
-                const int i = base + lane;
-                const uint64_t key = warp_sort32(i < n ? queue[i] : kPadKey, lane);
-                acc = warp_lower32(acc, key, lane);
-            }
-            __syncthreads();
-            queue[tid] = acc;
-            __syncthreads();
-            if (w == 0) {
-                uint64_t a = queue[lane];
-                for (int j = 1; j < THREADS / 32; j++) a = warp_lower32(a, queue[j * 32 + lane], lane);
-                queue[lane] = a;
-            }
-            __syncthreads();
+        } else if (k <= 32 && THREADS <= cap) {
+            reduce_queue<1, THREADS>(queue, n);
+        } else if (k <= 64 && 2 * THREADS <= cap) {
+            reduce_queue<2, THREADS>(queue, n);
+        } else if (k <= 128 && 4 * THREADS <= cap) {
+            reduce_queue<4, THREADS>(queue, n);
         } else {
             int P = 1;
             while (P < n) P <<= 1;
