@@ -339,11 +339,16 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, stage_acc = [], {}
     barrier()
+    profile_range = os.environ.get("B200_BENCH_PROFILE") == "1"   # ncu --profile-from-start off: timed steps only
+    if profile_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ev0.record()
     for _ in range(args.steps):
         step_device()
     ev1.record()
     barrier()
+    if profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = faiss.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
