@@ -180,11 +180,32 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
         uint4 c2 = skew_load_code16(lp, 256u + tid, n);           // code 1
         uint4 c3;
 
-        // a2: residuals of both queries against the list's centroid
+        // LUT build, specialised path: the PQ centroid slices of entries i (code value lc0 + 16 i) are loaded two
+        // entries ahead of their use; the first two do not even wait for the residuals
+#define DUO_LUT_LOAD(PV, I)                                                                        \
+    {                                                                                              \
+        const float* pc_ = pq_t + static_cast<int64_t>(lc0 + 16 * (I)) * (DSUB * M) + lm;          \
+        _Pragma("unroll") for (int j = 0; j < DSUB; j++) PV[j] = __ldg(pc_ + j * M);               \
+    }
+#define DUO_LUT_EMIT(PV, I)                                                                        \
+    {                                                                                              \
+        const uint64_t e_ = pack_f32x2(lut_entry_regs<DSUB>(PV, ra2), lut_entry_regs<DSUB>(PV, rb2)); \
+        uint64_t* row_ = lut2 + (lc0 + 16 * (I)) * kDuoRowEntries + lm;                            \
+        row_[0] = e_;                                                                              \
+        row_[16] = e_;                                                                             \
+    }
+        float pv0[DSUB ? DSUB : 1], pv1[DSUB ? DSUB : 1], pv2[DSUB ? DSUB : 1], pv3[DSUB ? DSUB : 1];
+        if constexpr (DSUB != 0) {
+            DUO_LUT_LOAD(pv0, 0)
+            DUO_LUT_LOAD(pv1, 1)
+        }
+        // a2: residuals of both queries against the list's centroid.  Specialised path: stored j-major
+        // (res[j * 16 + m]) so that the 16 lanes of a half-warp read consecutive words in the LUT build
         for (int j = tid; j < p.d; j += kThreads) {
             const float cj = p.cent[static_cast<int64_t>(list) * p.d + j];
-            res_a[j] = __fsub_rn(p.xq[static_cast<int64_t>(qa) * p.d + j], cj);
-            res_b[j] = __fsub_rn(p.xq[static_cast<int64_t>(qb) * p.d + j], cj);
+            const int dst = DSUB ? (j % (DSUB ? DSUB : 1)) * M + j / (DSUB ? DSUB : 1) : j;
+            res_a[dst] = __fsub_rn(p.xq[static_cast<int64_t>(qa) * p.d + j], cj);
+            res_b[dst] = __fsub_rn(p.xq[static_cast<int64_t>(qb) * p.d + j], cj);
         }
         const uint32_t ext_a = *reinterpret_cast<volatile uint32_t*>(p.qthr + qa);
         const uint32_t ext_b = *reinterpret_cast<volatile uint32_t*>(p.qthr + qb);
@@ -198,21 +219,24 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
             uint64_t ra2[DSUB / 2], rb2[DSUB / 2];
 #pragma unroll
             for (int j = 0; j < DSUB / 2; j++) {
-                ra2[j] = pack_f32x2(res_a[lm * DSUB + 2 * j], res_a[lm * DSUB + 2 * j + 1]);
-                rb2[j] = pack_f32x2(res_b[lm * DSUB + 2 * j], res_b[lm * DSUB + 2 * j + 1]);
+                ra2[j] = pack_f32x2(res_a[(2 * j) * M + lm], res_a[(2 * j + 1) * M + lm]);
+                rb2[j] = pack_f32x2(res_b[(2 * j) * M + lm], res_b[(2 * j + 1) * M + lm]);
             }
-#pragma unroll 4
-            for (int i = 0; i < 16; i++) {
-                const int c = lc0 + 16 * i;
-                const float* pc = pq_t + static_cast<int64_t>(c) * (DSUB * M) + lm;
-                float pv[DSUB];
-#pragma unroll
-                for (int j = 0; j < DSUB; j++) pv[j] = __ldg(pc + j * M);
-                const uint64_t e = pack_f32x2(lut_entry_regs<DSUB>(pv, ra2), lut_entry_regs<DSUB>(pv, rb2));
-                uint64_t* row = lut2 + c * kDuoRowEntries + lm;
-                row[0] = e;
-                row[16] = e;
+#pragma unroll 1
+            for (int i = 0; i < 16; i += 4) {
+                DUO_LUT_LOAD(pv2, i + 2)
+                DUO_LUT_LOAD(pv3, i + 3)
+                DUO_LUT_EMIT(pv0, i)
+                DUO_LUT_EMIT(pv1, i + 1)
+                if (i + 4 < 16) {
+                    DUO_LUT_LOAD(pv0, i + 4)
+                    DUO_LUT_LOAD(pv1, i + 5)
+                }
+                DUO_LUT_EMIT(pv2, i + 2)
+                DUO_LUT_EMIT(pv3, i + 3)
             }
+#undef DUO_LUT_LOAD
+#undef DUO_LUT_EMIT
         } else {
             for (int i = 0; i < 16; i++) {
                 const int c = lc0 + 16 * i;
