@@ -414,6 +414,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.nprobe = nprobe;
         sp.k = k;
         sp.nseg = nseg;
+        sp.negzero2 = 0x8000000080000000ull;
         const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
         if (h->scan_variant >= 2 && !use_skew)

@@ -107,9 +107,30 @@ __device__ __forceinline__ float lut_entry_regs(const float (&pv)[DSUB], const u
 }
 
 // NOTE on packed arithmetic: ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 (even with
-// -fmad=false), which would break bit-parity with the oracle's separately rounded multiply and add.  The LUT entry
-// therefore packs the subtract and the multiply only and accumulates with scalar adds (lut_entry_regs); the parity
-// tests compare every distance bit for bit and caught exactly this when it was tried.
+// -fmad=false), which would break bit-parity with the oracle's separately rounded multiply and add (the parity
+// tests compare every distance bit for bit and caught exactly this).  The square is therefore written as
+// fma(d, d, -0.0) with the -0.0 coming from a kernel parameter (opaque to ptxas): x*y + (-0.0) rounds exactly like
+// x*y, and an FFMA2 cannot be fused with the add that follows.
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// (T_a, T_b) for one (m, c) entry, packed across the two QUERIES: rab[j] = (r_a[j], r_b[j]); the PQ centroid value
+// p_j is broadcast to both halves (FADD2's scalar operand form).  Per dimension: FADD2 (sub), FFMA2 (square), FADD2
+// (accumulate) -- each half rounds exactly like the oracle's scalar sub / mul / add, j ascending.
+template <int DSUB>
+__device__ __forceinline__ uint64_t lut_entry_duo(const float (&pv)[DSUB], const uint64_t (&rab)[DSUB],
+                                                  uint64_t negzero2) {
+    uint64_t acc = 0ull;
+#pragma unroll
+    for (int j = 0; j < DSUB; j++) {
+        const uint64_t d2 = sub_f32x2(rab[j], pack_f32x2(pv[j], pv[j]));
+        acc = add_f32x2(acc, fma_f32x2(d2, d2, negzero2));
+    }
+    return acc;
+}
 
 // DSUB = d / 16 when it is one of the specialised values (residual slices held in registers), 0 = generic.
 template <int DSUB>
@@ -189,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
     }
 #define DUO_LUT_EMIT(PV, I)                                                                        \
     {                                                                                              \
-        const uint64_t e_ = pack_f32x2(lut_entry_regs<DSUB>(PV, ra2), lut_entry_regs<DSUB>(PV, rb2)); \
+        const uint64_t e_ = lut_entry_duo<DSUB>(PV, rab, negzero2);                                \
         uint64_t* row_ = lut2 + (lc0 + 16 * (I)) * kDuoRowEntries + lm;                            \
         row_[0] = e_;                                                                              \
         row_[16] = e_;                                                                             \
@@ -199,13 +220,18 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
             DUO_LUT_LOAD(pv0, 0)
             DUO_LUT_LOAD(pv1, 1)
         }
-        // a2: residuals of both queries against the list's centroid.  Specialised path: stored j-major
-        // (res[j * 16 + m]) so that the 16 lanes of a half-warp read consecutive words in the LUT build
+        // a2: residuals of both queries against the list's centroid.  Specialised path: stored as pairs (r_a, r_b),
+        // j-major (pair j * 16 + m), so that a half-warp reads 16 consecutive pairs in the LUT build
         for (int j = tid; j < p.d; j += kThreads) {
             const float cj = p.cent[static_cast<int64_t>(list) * p.d + j];
-            const int dst = DSUB ? (j % (DSUB ? DSUB : 1)) * M + j / (DSUB ? DSUB : 1) : j;
-            res_a[dst] = __fsub_rn(p.xq[static_cast<int64_t>(qa) * p.d + j], cj);
-            res_b[dst] = __fsub_rn(p.xq[static_cast<int64_t>(qb) * p.d + j], cj);
+            const float ra = __fsub_rn(p.xq[static_cast<int64_t>(qa) * p.d + j], cj);
+            const float rb = __fsub_rn(p.xq[static_cast<int64_t>(qb) * p.d + j], cj);
+            if (DSUB) {
+                reinterpret_cast<uint64_t*>(res_a)[(j % (DSUB ? DSUB : 1)) * M + j / (DSUB ? DSUB : 1)] = pack_f32x2(ra, rb);
+            } else {
+                res_a[j] = ra;
+                res_b[j] = rb;
+            }
         }
         const uint32_t ext_a = *reinterpret_cast<volatile uint32_t*>(p.qthr + qa);
         const uint32_t ext_b = *reinterpret_cast<volatile uint32_t*>(p.qthr + qb);
@@ -216,12 +242,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
         __syncthreads();
         // a3: both LUTs, interleaved; the PQ centroid slice is loaded once for the two queries
         if constexpr (DSUB != 0) {
-            uint64_t ra2[DSUB / 2], rb2[DSUB / 2];
+            uint64_t rab[DSUB];
 #pragma unroll
-            for (int j = 0; j < DSUB / 2; j++) {
-                ra2[j] = pack_f32x2(res_a[(2 * j) * M + lm], res_a[(2 * j + 1) * M + lm]);
-                rb2[j] = pack_f32x2(res_b[(2 * j) * M + lm], res_b[(2 * j + 1) * M + lm]);
-            }
+            for (int j = 0; j < DSUB; j++) rab[j] = reinterpret_cast<const uint64_t*>(res_a)[j * M + lm];
+            const uint64_t negzero2 = p.negzero2;
 #pragma unroll 1
             for (int i = 0; i < 16; i += 4) {
                 DUO_LUT_LOAD(pv2, i + 2)
