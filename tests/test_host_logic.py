@@ -155,3 +155,42 @@ def test_faiss_container_roundtrip(oracle, tmp_path):
             _util.assert_bit_equal(z[key], a[key], key)
     with pytest.raises(RuntimeError):
         parse_faiss_ivfpq(b"IxF2" + bytes(64))
+
+
+def test_sass_is_blackwell_native_and_exact():
+    """Static evidence from the built library (cuobjdump, no GPU needed): the coarse GEMM uses tcgen05 / TMEM / TMA,
+    the two-query scan uses LDS.64 + FFMA2, and no kernel on the exact-arithmetic path contains a contracted
+    multiply-add it did not ask for (ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2: see scan_duo.cuh)."""
+    import shutil
+    import subprocess
+    import b200ivfpq
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", b200ivfpq.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            funcs[cur].append(line)
+
+    def ops(substr):
+        names = [n for n in funcs if substr in n]
+        assert names, f"no kernel matching {substr}"
+        return names, "\n".join("\n".join(funcs[n]) for n in names)
+
+    _, gemm = ops("coarse_tc_gemm_kernel")
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
+        assert mnemonic in gemm, f"{mnemonic} missing from the coarse GEMM"
+    names, _ = ops("scan_duo16_kernelILi8E")
+    duo = "\n".join(funcs[names[0]])
+    assert duo.count("LDS.64") >= 16 * 7 and duo.count("FFMA2") >= 2 * 16 * 7      # 7 unrolled 16-step blocks
+    assert "FMUL2" not in duo or duo.count("FFMA2") % 32 == 0
+    # exact kernels never use a scalar FFMA that the source did not write (__fmaf_rn appears only in the one-query
+    # scan's 0/1-multiplier accumulate); the LUT / distance arithmetic must stay FADD / FMUL / FADD2 / FMUL2
+    # (coarse_rescore_kernel is left out: its sqrtf for the error bound legitimately expands to FFMA)
+    for kern in ("coarse_dist_kernel", "encode_kernel", "coarse_exact_flagged_kernel"):
+        _, text = ops(kern)
+        assert not re.search(r"\bFFMA\b", text), f"contracted FFMA in {kern}"
