@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "scan_skew.cuh"
 #include "scan_duo.cuh"
+#include "scan_duo32.cuh"
 #include "coarse_tc.cuh"
 #include "select_radix.cuh"
 
@@ -340,6 +341,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         const int64_t pairs = std::min<int64_t>(qb, nq) * nprobe;
         const int64_t target = 2 * (int64_t)h->num_sms;
         if (pairs < target) nseg = (int)std::min<int64_t>(16, (target + pairs - 1) / pairs);
+        if (h->scan_variant == 3) nseg = 1;   // forced two-query kernels (tests): they scan whole lists
         if (h->force_nseg > 0) nseg = h->force_nseg;
     }
 
@@ -417,7 +419,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.negzero2 = 0x8000000080000000ull;
         const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
-        if (h->scan_variant >= 2 && !use_skew)
+        if (h->scan_variant >= 2 && !use_skew && !(h->scan_variant == 3 && duo32_supported(h->M, h->d, k)))
             return fail(B200_IVFPQ_EUNSUPPORTED, "skewed scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
         // two queries per work item pay off once lists are shared: on average >= 3 probing queries per list
         bool use_duo = use_skew && nseg == 1 && h->scan_variant != 2 &&
@@ -428,6 +430,13 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
                                           cudaGetErrorString(cudaGetLastError()));
                 return rc;
             }
+            g_launches.fetch_add(1);
+        } else if (duo32_supported(h->M, h->d, k) && aligned16 && nseg == 1 && h->scan_variant != 1 &&
+                   h->scan_variant != 2 && (h->scan_variant == 3 || npairs >= 3 * h->nlist) &&
+                   (rc = launch_scan_duo32(sp, h->pq_t.as<float>(), npairs, h->num_sms, st)) != -2) {
+            // M = 32: two queries per work item, two alternating tables (scan_duo32.cuh)
+            if (rc == -1) return fail(B200_IVFPQ_ECUDA, "two-query M=32 scan launch failed: %s",
+                                      cudaGetErrorString(cudaGetLastError()));
             g_launches.fetch_add(1);
         } else if (use_skew) {
             if ((rc = launch_scan_skew(sp, h->pq_t.as<float>(), npairs, h->num_sms, st))) {

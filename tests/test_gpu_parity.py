@@ -120,6 +120,26 @@ def test_two_query_scan_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
         _util.assert_bit_equal(I, Ir, "I (duo)")
 
 
+@pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used", [
+    (128, 24, 40000, 101, 5, 10, None),     # C5 shape (dsub 4), odd group sizes, several tiles per list
+    (256, 16, 9000, 64, 16, 100, 13),       # dsub 8, k = 100, empty lists
+    (512, 8, 3000, 1, 8, 10, None),         # dsub 16 (RALM-S shape), one query: every group is a single
+    (768, 12, 5000, 37, 3, 7, None),        # dsub 24: generic LUT build
+    (64, 6, 700, 20, 6, 10, None),          # dsub 2, lists shorter than one 512-code iteration
+])
+def test_two_query_scan_kernel_m32(oracle, d, nlist, n, nq, nprobe, k, used):
+    """scan_duo32.cuh: M = 32, two alternating look-up tables, two queries per work item."""
+    a = _util.make_index_arrays(oracle, 70 + d, d, nlist, 32, n, used_lists=used)
+    xq = _util.make_queries(13, a, nq)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+    index = _load(a, "duo")
+    index.nprobe = nprobe
+    for _ in range(2):
+        D, I = index.search(xq, k)
+        _util.assert_bit_equal(D, Dr, "D (duo32)")
+        _util.assert_bit_equal(I, Ir, "I (duo32)")
+
+
 def test_search_preassigned(oracle):
     import b200ivfpq as faiss
     a = _util.make_index_arrays(oracle, 9, 128, 20, 16, 6000)
