@@ -16,6 +16,7 @@
 #include "scan_skew.cuh"
 #include "scan_duo.cuh"
 #include "scan_duo32.cuh"
+#include "scan_quad.cuh"
 #include "coarse_tc.cuh"
 #include "select_radix.cuh"
 
@@ -82,6 +83,10 @@ struct DevBuf {
 
 constexpr size_t kCoarseMatrixBudget = size_t(3) << 30;   // bytes of coarse distances per query chunk
 constexpr size_t kPairOutBudget = size_t(2) << 30;        // bytes of per-pair candidates per query chunk
+// The four-query filter kernel halves the per-code cost of the two-query kernel but has the higher cost per work
+// item (four LUTs, exact LUT to global memory, survivor drains): it wins once lists are a few thousand codes long
+// (measured on the C2 shape: 12.2k-code lists 9.5 vs 12.5 ms, 1.5k-code lists 4.9 vs 4.1 ms).
+constexpr int64_t kQuadMinAvgList = 4096;
 
 }  // namespace
 
@@ -94,10 +99,12 @@ struct b200_ivfpq_index {
     const int64_t* ids = nullptr;
     bool has_lists = false;
     int device = 0, num_sms = 148;
-    int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free), 3 = two-query skewed (scan_duo.cuh)
+    int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free), 3 = two-query skewed (scan_duo.cuh),
+                            // 4 = four-query integer filter + exact survivors (scan_quad.cuh)
+    int64_t max_list = 0;   // longest inverted list
     int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
     // workspace
-    DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t;
+    DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t, lutf, pq_maxnorm;
     DevBuf host_xq, host_D, host_I;
     // tensor-core coarse quantizer (K1): split-bf16 centroids, norms, per-call buffers
     DevBuf cent_bf16, cnorm, cmax2, q_bf16, qnorm, cand, cand_score, cand_cnt, flags, nflagged;
@@ -341,7 +348,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         const int64_t pairs = std::min<int64_t>(qb, nq) * nprobe;
         const int64_t target = 2 * (int64_t)h->num_sms;
         if (pairs < target) nseg = (int)std::min<int64_t>(16, (target + pairs - 1) / pairs);
-        if (h->scan_variant == 3) nseg = 1;   // forced two-query kernels (tests): they scan whole lists
+        if (h->scan_variant >= 3) nseg = 1;   // forced multi-query kernels (tests): they scan whole lists
         if (h->force_nseg > 0) nseg = h->force_nseg;
     }
 
@@ -351,7 +358,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     if ((rc = h->hist.ensure(sizeof(int) * h->nlist))) return rc;
     if ((rc = h->start.ensure(sizeof(int) * h->nlist))) return rc;
     if ((rc = h->gstart.ensure(sizeof(int) * h->nlist))) return rc;
-    if ((rc = h->groups.ensure(sizeof(DuoGroup) * qb * nprobe))) return rc;
+    if ((rc = h->groups.ensure(sizeof(QuadGroup) * qb * nprobe))) return rc;
     if ((rc = h->order.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
     if ((rc = h->out_keys.ensure(sizeof(uint64_t) * qb * nprobe * k * nseg))) return rc;
     if ((rc = h->out_cnt.ensure(sizeof(int) * qb * nprobe * nseg))) return rc;
@@ -377,6 +384,18 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         }
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[2], st));
 
+        // which scan kernel will run decides how pairs are grouped (2 or 4 queries of a list per work item)
+        const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
+        int quad_ctas = 0;
+        if (quad_supported(h->M, h->d, k) && aligned16 && nseg == 1 && h->max_list < (int64_t)kQuadMaxList &&
+            (h->scan_variant == 4 ||
+             (h->scan_variant == 0 && npairs >= 6 * h->nlist && h->ntotal >= kQuadMinAvgList * h->nlist)))
+            quad_ctas = quad_grid(h->dsub, h->d, k, npairs, h->num_sms);
+        if (h->scan_variant == 4 && quad_ctas == 0)
+            return fail(B200_IVFPQ_EUNSUPPORTED, "four-query scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
+        const int gsz = quad_ctas ? 4 : 2;
+        if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * kQuadScratchFloat4 * quad_ctas))) return rc;
+
         // pair setup
         CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * h->nlist, st));
         CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs * nseg, st));
@@ -386,13 +405,14 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         pair_hist_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
                                                              h->hist.as<int>(), stats);
         LAUNCH_CHECK();
-        pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), h->nlist, stats);
+        pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), h->nlist, gsz,
+                                             stats);
         LAUNCH_CHECK();
-        CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, sizeof(DuoGroup) * npairs, st));
+        CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, (gsz == 4 ? sizeof(QuadGroup) : sizeof(DuoGroup)) * npairs, st));
         pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
                                                                 h->start.as<int>(), h->gstart.as<int>(),
-                                                                h->hist.as<int>(), h->order.as<int32_t>(),
-                                                                h->groups.as<DuoGroup>());
+                                                                h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p,
+                                                                gsz);
         LAUNCH_CHECK();
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));
 
@@ -405,7 +425,9 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.codes = h->codes;
         sp.probe = probe32;
         sp.order = h->order.as<int32_t>();
-        sp.groups = h->groups.as<DuoGroup>();
+        sp.groups = h->groups.p;
+        sp.lutf_scratch = h->lutf.as<float4>();
+        sp.pq_maxnorm = h->pq_maxnorm.as<float>();
         sp.out_keys = h->out_keys.as<uint64_t>();
         sp.out_cnt = h->out_cnt.as<int>();
         sp.qthr = h->qthr.as<uint32_t>();
@@ -417,14 +439,18 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.k = k;
         sp.nseg = nseg;
         sp.negzero2 = 0x8000000080000000ull;
-        const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
-        if (h->scan_variant >= 2 && !use_skew && !(h->scan_variant == 3 && duo32_supported(h->M, h->d, k)))
+        if (h->scan_variant >= 2 && h->scan_variant != 4 && !use_skew &&
+            !(h->scan_variant == 3 && duo32_supported(h->M, h->d, k)))
             return fail(B200_IVFPQ_EUNSUPPORTED, "skewed scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
         // two queries per work item pay off once lists are shared: on average >= 3 probing queries per list
         bool use_duo = use_skew && nseg == 1 && h->scan_variant != 2 &&
                        (h->scan_variant == 3 || npairs >= 3 * h->nlist);
-        if (use_duo) {
+        if (quad_ctas) {
+            if ((rc = launch_scan_quad(sp, h->pq_t.as<float>(), quad_ctas, st)))
+                return fail(B200_IVFPQ_ECUDA, "four-query scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            g_launches.fetch_add(1);
+        } else if (use_duo) {
             if ((rc = launch_scan_duo(sp, h->pq_t.as<float>(), npairs, h->num_sms, st))) {
                 if (rc == -1) return fail(B200_IVFPQ_ECUDA, "two-query scan launch failed: %s",
                                           cudaGetErrorString(cudaGetLastError()));
@@ -507,7 +533,7 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     CUDA_TRY(cudaGetDevice(&h->device));
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     const char* v = getenv("B200_IVFPQ_SCAN");
-    if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : !strcmp(v, "duo") ? 3 : 0;
+    if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : !strcmp(v, "duo") ? 3 : !strcmp(v, "quad") ? 4 : 0;
     v = getenv("B200_IVFPQ_GRAPH");
     if (v) h->use_graph = atoi(v) != 0;
     v = getenv("B200_IVFPQ_NSEG");
@@ -521,7 +547,7 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
 int b200_ivfpq_destroy(b200_ivfpq_t h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t, &h->gstart, &h->groups,
+    DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t, &h->gstart, &h->groups, &h->lutf, &h->pq_maxnorm,
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
                       &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
                       &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged, &h->cand_cnt};
@@ -569,6 +595,9 @@ int b200_ivfpq_set_codebooks(b200_ivfpq_t h, const float* d_centroids, const flo
     if (rc) return rc;
     pq_transpose_kernel<<<grid1d(total, 256), 256>>>(d_pq, h->pq_t.as<float>(), h->M, h->dsub);
     LAUNCH_CHECK();
+    if ((rc = h->pq_maxnorm.ensure(sizeof(float) * h->M))) return rc;
+    pq_maxnorm_kernel<<<h->M, 256>>>(d_pq, h->dsub, h->pq_maxnorm.as<float>());   // scan_quad.cuh's quantisation bound
+    LAUNCH_CHECK();
     CUDA_TRY(cudaDeviceSynchronize());
     return 0;
 }
@@ -579,8 +608,10 @@ int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, const uint8_t
     if (!h_offsets) return fail(B200_IVFPQ_EINVAL, "null offsets");
     if (ntotal < 0 || h_offsets[0] != 0 || h_offsets[h->nlist] != ntotal)
         return fail(B200_IVFPQ_EINVAL, "offsets must start at 0 and end at ntotal");
+    int64_t max_list = 0;
     for (int64_t l = 0; l < h->nlist; l++) {
         int64_t sz = h_offsets[l + 1] - h_offsets[l];
+        max_list = std::max(max_list, sz);
         if (sz < 0) return fail(B200_IVFPQ_EINVAL, "offsets not monotone at list %lld", (long long)l);
         if (sz >= (int64_t(1) << 32)) return fail(B200_IVFPQ_EUNSUPPORTED, "list %lld longer than 2^32", (long long)l);
     }
@@ -592,6 +623,7 @@ int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, const uint8_t
     h->codes = d_codes;
     h->ids = d_ids;
     h->ntotal = ntotal;
+    h->max_list = max_list;
     h->has_lists = true;
     h->state_epoch++;
     return 0;

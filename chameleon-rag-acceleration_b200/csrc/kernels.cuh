@@ -112,7 +112,8 @@ struct PairStats {
     unsigned long long scan_codes;   // sum over valid pairs of list_size
     int nvalid;                      // number of pairs with a non-empty list
     int work_counter;                // dynamic scheduler of scan_pairs_kernel
-    int ngroups;                     // number of same-list pair groups (scan_duo.cuh), sum over lists of ceil(cnt / 2)
+    int ngroups;                     // number of same-list pair groups (scan_duo.cuh / scan_quad.cuh), sum over lists
+                                     // of ceil(cnt / group size)
 };
 
 __global__ void pair_hist_kernel(const int32_t* __restrict__ probe, int64_t npairs,
@@ -139,7 +140,7 @@ __global__ void pair_hist_kernel(const int32_t* __restrict__ probe, int64_t npai
 // hist is zeroed on the way out so that pair_scatter_kernel can use it as its per-list cursor.
 // Single CTA (nlist <= a few 100k).
 __global__ void __launch_bounds__(1024) pair_scan_kernel(int* __restrict__ hist, int* __restrict__ start,
-                                                         int* __restrict__ gstart, int64_t nlist,
+                                                         int* __restrict__ gstart, int64_t nlist, int gsz,
                                                          PairStats* __restrict__ stats) {
     __shared__ int warp_sums[32], warp_gsums[32];
     __shared__ int carry, gcarry;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(int* __restrict__ hist,
     for (int64_t base = 0; base < nlist; base += 1024) {
         int64_t i = base + tid;
         int v = i < nlist ? hist[i] : 0;
-        int gv = (v + 1) >> 1;
+        int gv = (v + gsz - 1) / gsz;
         int x = v, gx = gv;
         for (int o = 1; o < 32; o <<= 1) {
             int y = __shfl_up_sync(0xffffffffu, x, o);
@@ -214,13 +215,23 @@ struct __align__(16) DuoGroup {
 };
 static_assert(sizeof(DuoGroup) == 32, "DuoGroup is two 16-byte words");
 
+// One work item of the four-query filter scan (scan_quad.cuh): up to four pairs of the same list.
+struct __align__(16) QuadGroup {
+    int pair[4];    // -1: unused slot (always at the end)
+    int list;
+    uint32_t n;     // list length (> 0)
+    int64_t beg;    // first row of the list in codes / ids
+    int64_t pad_[2];
+};
+static_assert(sizeof(QuadGroup) == 48, "QuadGroup is three 16-byte words");
+
 // order[] = pair indices sorted by list; groups[] = the same pairs two by two (pair_b is pre-set to -1 by a 0xff
 // memset, so the odd pair of a list keeps it).  Which queries end up together depends on the atomics' order; the
 // results do not.
 __global__ void pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t npairs,
                                     const int64_t* __restrict__ offsets, const int* __restrict__ start,
                                     const int* __restrict__ gstart, int* __restrict__ cursor,
-                                    int32_t* __restrict__ order, DuoGroup* __restrict__ groups) {
+                                    int32_t* __restrict__ order, void* __restrict__ groups, int gsz) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     int l = probe[i];
@@ -229,7 +240,17 @@ __global__ void pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t n
     if (sz <= 0) return;
     const int rank = atomicAdd(&cursor[l], 1);
     order[start[l] + rank] = static_cast<int32_t>(i);
-    DuoGroup* g = groups + gstart[l] + (rank >> 1);
+    if (gsz == 4) {
+        QuadGroup* g = static_cast<QuadGroup*>(groups) + gstart[l] + (rank >> 2);
+        g->pair[rank & 3] = static_cast<int32_t>(i);
+        if ((rank & 3) == 0) {
+            g->list = l;
+            g->n = static_cast<uint32_t>(sz);
+            g->beg = beg;
+        }
+        return;
+    }
+    DuoGroup* g = static_cast<DuoGroup*>(groups) + gstart[l] + (rank >> 1);
     if (rank & 1) {
         g->pair_b = static_cast<int32_t>(i);
     } else {
@@ -264,7 +285,9 @@ struct ScanParams {
     const uint8_t* codes;     // (ntotal, M)
     const int32_t* probe;     // (nq * nprobe) list id or -1
     const int32_t* order;     // (nvalid) pair indices sorted by list
-    const DuoGroup* groups;   // (ngroups) work items of the two-query scan (scan_duo.cuh)
+    const void* groups;       // (ngroups) work items: DuoGroup (scan_duo.cuh, scan_duo32.cuh) or QuadGroup (scan_quad.cuh)
+    float4* lutf_scratch;     // scan_quad.cuh: one fp32 LUT set (16 x 256 float4) per CTA, global memory
+    const float* pq_maxnorm;  // scan_quad.cuh: (M) max_c ||pq[m][c]||, slightly rounded up
     uint64_t* out_keys;       // (nq * nprobe, k)
     int* out_cnt;             // (nq * nprobe), pre-zeroed
     uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf

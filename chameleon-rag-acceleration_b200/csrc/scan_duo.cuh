@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
     int next_work = 0, buf = 0;
     if (tid == 0) {
         next_work = atomicAdd(&p.stats->work_counter, 1);
-        if (next_work < ngroups) duo_copy_group_async(&s_grp[0], p.groups + next_work);
+        if (next_work < ngroups) duo_copy_group_async(&s_grp[0], static_cast<const DuoGroup*>(p.groups) + next_work);
     }
     for (;;) {
         if (tid == 0) {
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_duo16_kernel(const ScanParam
         }
         __syncthreads();
         buf ^= 1;
-        if (tid == 0 && next_work < ngroups) duo_copy_group_async(&s_grp[buf], p.groups + next_work);
+        if (tid == 0 && next_work < ngroups) duo_copy_group_async(&s_grp[buf], static_cast<const DuoGroup*>(p.groups) + next_work);
 
         // a4 + a5.  Iteration `it` processes block b = it - 1 (it = 0 is the prologue that only feeds bytes
         // 0..r-1 of code 0).  Four iterations per tile, fully unrolled so that the code ring needs no moves.

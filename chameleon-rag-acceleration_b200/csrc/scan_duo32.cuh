@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kDuo32Threads, 1) scan_duo32_kernel(const Scan
     int next_work = 0, buf = 0;
     if (tid == 0) {
         next_work = atomicAdd(&p.stats->work_counter, 1);
-        if (next_work < ngroups) duo_copy_group_async(&s_grp[0], p.groups + next_work);
+        if (next_work < ngroups) duo_copy_group_async(&s_grp[0], static_cast<const DuoGroup*>(p.groups) + next_work);
     }
     for (;;) {
         if (tid == 0) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kDuo32Threads, 1) scan_duo32_kernel(const Scan
         }
         __syncthreads();
         buf ^= 1;
-        if (tid == 0 && next_work < ngroups) duo_copy_group_async(&s_grp[buf], p.groups + next_work);
+        if (tid == 0 && next_work < ngroups) duo_copy_group_async(&s_grp[buf], static_cast<const DuoGroup*>(p.groups) + next_work);
 
         // a4 + a5.  Iteration it: odd block (code it-1 . hi | code it . lo) finishes code it-1, even block walks code it.
         // it = 0 is the prologue (code -1 = zeros), it = nblk finishes the last codes and needs no even block.

@@ -258,4 +258,73 @@ struct TopK {
     }
 };
 
+// Fold NQ queues at once when every one of them holds at most 32 pending keys (the common case once thresholds are
+// known): warp q sorts queue q in registers, THREADS / NQ threads merge it into its best list -- three barriers for
+// all queues together instead of three per queue.  Returns false, having done nothing, when some queue holds more
+// (the caller then folds them one by one).  All THREADS threads call, after a barrier; THREADS >= 32 NQ.
+template <int THREADS, int NQ>
+__device__ __forceinline__ bool topk_fold_small(TopK (&tk)[NQ], const uint32_t (&ext)[NQ]) {
+    static_assert(THREADS % NQ == 0 && THREADS / 32 >= NQ, "one warp per queue");
+    constexpr int PER = THREADS / NQ;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, part = tid / PER, tl = tid % PER;
+    int n[NQ];
+    bool small = true, any = false;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        n[q] = tk[q].meta[1];
+        small = small && n[q] <= 32;
+        any = any || n[q] > 0;
+    }
+    if (!small) return false;   // uniform: every thread read the same counters
+    if (!any) return true;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        if (w == q && n[q] > 0) {
+            const uint64_t key = TopK::warp_sort32(lane < n[q] ? tk[q].queue[lane] : kPadKey, lane);
+            tk[q].queue[lane] = key;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        if (part == q && n[q] > 0) {
+            const int k = tk[q].k, cur = tk[q].meta[2], nb = tk[q].meta[0];
+            const uint64_t* old = tk[q].best + cur * k;
+            uint64_t* out = tk[q].best + (cur ^ 1) * k;
+            const uint64_t* queue = tk[q].queue;
+            const int nnew = n[q] < k ? n[q] : k;
+            for (int i = tl; i < nnew; i += PER) {
+                const uint64_t key = queue[i];
+                const int r = i + TopK::lower_bound(old, nb, key);
+                if (r < k) out[r] = key;
+            }
+            for (int t = tl; t < nb; t += PER) {
+                const uint64_t key = old[t];
+                const int r = t + TopK::lower_bound(queue, nnew, key);
+                if (r < k) out[r] = key;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        if (tid == q * PER && n[q] > 0) {
+            const int k = tk[q].k, cur = tk[q].meta[2], nb = tk[q].meta[0];
+            const uint64_t* out = tk[q].best + (cur ^ 1) * k;
+            const int nn = nb + n[q] < k ? nb + n[q] : k;
+            tk[q].meta[0] = nn;
+            tk[q].meta[1] = 0;
+            tk[q].meta[2] = cur ^ 1;
+            uint32_t thr = ext[q];
+            if (nn == k) {
+                const uint32_t kth = static_cast<uint32_t>(out[k - 1] >> 32);
+                thr = kth < thr ? kth : thr;
+            }
+            tk[q].meta[3] = static_cast<int>(thr);
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 }  // namespace b200

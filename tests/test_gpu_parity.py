@@ -71,7 +71,7 @@ def test_search_bit_exact(oracle, d, nlist, M, n, nq, nprobe, k, used):
     _util.assert_bit_equal(It.cpu().numpy(), Ir, "I (device path)")
 
 
-@pytest.mark.parametrize("variant", ["generic", "skew", "duo"])
+@pytest.mark.parametrize("variant", ["generic", "skew", "duo", "quad"])
 def test_both_scan_kernels_agree_with_oracle(oracle, variant):
     a = _util.make_index_arrays(oracle, 5, 128, 48, 16, 30000)
     xq = _util.make_queries(8, a, 50)
@@ -83,7 +83,7 @@ def test_both_scan_kernels_agree_with_oracle(oracle, variant):
     _util.assert_bit_equal(I, Ir, f"I ({variant})")
 
 
-@pytest.mark.parametrize("variant", ["generic", "skew", "duo"])
+@pytest.mark.parametrize("variant", ["generic", "skew", "duo", "quad"])
 def test_ties_follow_scan_order(oracle, variant):
     """Many duplicate codes -> equal distances; (distance, probe rank, offset) order must match the oracle."""
     rng = np.random.default_rng(3)
@@ -118,6 +118,30 @@ def test_two_query_scan_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
         D, I = index.search(xq, k)
         _util.assert_bit_equal(D, Dr, "D (duo)")
         _util.assert_bit_equal(I, Ir, "I (duo)")
+
+
+@pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used", [
+    (128, 24, 60000, 103, 5, 10, None),     # group sizes 1..4, several tiles per list
+    (96, 16, 12000, 64, 16, 100, 13),       # dsub 6, k = 100, empty lists, every query probes every list
+    (64, 8, 3000, 1, 8, 10, None),          # one query: every group is a single
+    (256, 12, 5000, 37, 3, 7, None),        # dsub 16: generic LUT build
+    (128, 4, 9000, 200, 4, 1, None),        # k = 1, 200 queries on every list
+])
+def test_four_query_filter_scan_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
+    """scan_quad.cuh: integer lower-bound filter + exact evaluation of the survivors.  Must return exactly the oracle's
+    results, ties included (many duplicate codes make sure survivors at the threshold are not lost)."""
+    a = _util.make_index_arrays(oracle, 90 + d, d, nlist, 16, n, used_lists=used)
+    if d == 128 and nlist == 4:
+        rng = np.random.default_rng(5)
+        a["codes"] = np.ascontiguousarray(a["codes"][rng.integers(0, 500, size=a["codes"].shape[0])])   # heavy ties
+    xq = _util.make_queries(17, a, nq)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+    index = _load(a, "quad")
+    index.nprobe = nprobe
+    for _ in range(2):
+        D, I = index.search(xq, k)
+        _util.assert_bit_equal(D, Dr, "D (quad)")
+        _util.assert_bit_equal(I, Ir, "I (quad)")
 
 
 @pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used", [
