@@ -439,6 +439,10 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.k = k;
         sp.nseg = nseg;
         sp.negzero2 = 0x8000000080000000ull;
+        {
+            const char* v = getenv("B200_IVFPQ_QUAD_DRAIN");
+            sp.quad_drain_at = v ? std::max(0, std::min(256, atoi(v))) : 256;
+        }
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
         if (h->scan_variant >= 2 && h->scan_variant != 4 && !use_skew &&
             !(h->scan_variant == 3 && duo32_supported(h->M, h->d, k)))

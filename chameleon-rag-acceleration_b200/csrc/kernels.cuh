@@ -293,6 +293,7 @@ struct ScanParams {
     uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf
     PairStats* stats;
     int d, M, dsub, nprobe, k;
+    int quad_drain_at;        // scan_quad.cuh: survivors queued before the exact phase runs (<= 256)
     uint64_t negzero2;        // (-0.0f, -0.0f): an addend ptxas cannot see through (scan_duo.cuh lut_entry_duo)
     int nseg;                 // each (query, probe) pair is scanned by nseg CTAs (contiguous segments of its list):
                               // fills the GPU at small batch sizes; slot = pair * nseg + segment

@@ -34,7 +34,8 @@ namespace b200 {
 
 constexpr int kQuadLutBytes = 256 * 256;          // 256 code values x 32 periodic entries x 4 x u16
 constexpr int kQuadCap = 1024;                    // exact-candidate queue per query
-constexpr int kQuadSurvCap = 1280;                // survivor queue (u32 each): one tile of 1024 codes + 256
+constexpr int kQuadSurvMin = 1280;                // survivor queue (u32 each): one tile of 1024 codes + the drain trigger
+constexpr int kQuadSurvMax = 1280;
 constexpr int kQuadTB = 4;                        // blocks (of 32 codes) per warp per tile
 constexpr uint32_t kQuadMaxList = 1u << 28;       // survivor entry = (offset << 4) | query mask
 constexpr size_t kQuadScratchFloat4 = 16 * 256;   // exact LUT of one CTA in global memory: [m][c] float4
@@ -45,9 +46,20 @@ inline bool quad_supported(int M, int d, int k) {
 }
 
 // shared memory: [ lut16 | residuals (4 x dpad f32) | 4 x TopK | survivors | control ]
+__host__ __device__ inline size_t quad_smem_fixed(int d, int k) {
+    return kQuadLutBytes + 4 * sizeof(float) * static_cast<size_t>((d + 3) & ~3) + 4 * TopK::smem_bytes(k, kQuadCap) + 64 +
+           2 * sizeof(QuadGroup);
+}
+// survivor queue capacity: whatever two CTAs per SM leave (228 KB per SM, 1 KB reserved per CTA), in steps of 256
+__host__ __device__ inline int quad_surv_cap(int d, int k) {
+    const long long room = (228 * 1024 / 2 - 1024 - 256) - static_cast<long long>(quad_smem_fixed(d, k));
+    long long cap = room > 0 ? (room / 4) & ~255ll : 0;
+    if (cap > kQuadSurvMax) cap = kQuadSurvMax;
+    if (cap < kQuadSurvMin) cap = kQuadSurvMin;
+    return static_cast<int>(cap);
+}
 __host__ __device__ inline size_t quad_smem_bytes(int d, int k) {
-    return kQuadLutBytes + 4 * sizeof(float) * static_cast<size_t>((d + 3) & ~3) + 4 * TopK::smem_bytes(k, kQuadCap) +
-           sizeof(uint32_t) * kQuadSurvCap + 64 + 2 * sizeof(QuadGroup);
+    return quad_smem_fixed(d, k) + sizeof(uint32_t) * quad_surv_cap(d, k);
 }
 
 struct QuadCtrl {          // 64 bytes
@@ -136,7 +148,8 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
 #pragma unroll
     for (int q = 0; q < 4; q++) tk[q].bind(tk_base + q * TopK::smem_bytes(p.k, kQuadCap), p.k, kQuadCap);
     uint32_t* surv = reinterpret_cast<uint32_t*>(tk_base + 4 * TopK::smem_bytes(p.k, kQuadCap));
-    QuadCtrl* ctrl = reinterpret_cast<QuadCtrl*>(surv + kQuadSurvCap);
+    const int surv_cap = quad_surv_cap(p.d, p.k);
+    QuadCtrl* ctrl = reinterpret_cast<QuadCtrl*>(surv + surv_cap);
     QuadGroup* s_grp = reinterpret_cast<QuadGroup*>(ctrl + 1);
     float4* lutf = p.lutf_scratch + static_cast<size_t>(blockIdx.x) * kQuadScratchFloat4;   // exact LUT [m][c]
 
@@ -427,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
             if (t0 + 3 < nblk) QUAD_ITER(c3, c1, 3)
             // survivors of the next tile must fit: drain when more than one tile's worth is queued
             const int seen = *reinterpret_cast<volatile int*>(&ctrl->nsurv[sphase]);
-            if (__syncthreads_or(seen > kQuadSurvCap - kThreads * kQuadTB)) drain();
+            if (__syncthreads_or(seen > p.quad_drain_at)) drain();
         }
 #undef QUAD_ITER
         __syncthreads();
