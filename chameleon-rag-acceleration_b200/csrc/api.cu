@@ -19,6 +19,7 @@
 #include "scan_quad.cuh"
 #include "coarse_tc.cuh"
 #include "select_radix.cuh"
+#include "coarse_small.cuh"
 
 using namespace b200;
 
@@ -223,6 +224,25 @@ int run_tc_scores(b200_ivfpq_index* h, int64_t nq, const float* d_xq, float* d_s
 int run_coarse(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int nprobe, int32_t* probe32, int64_t* ids64,
                float* dis, cudaStream_t st, bool time_stages) {
     int rc;
+    if (h->coarse_variant == 0 && coarse_small_usable(nq, h->nlist, nprobe)) {
+        // latency path: exact distances + register top-32 per 128 centroids, then one select CTA per query
+        const int64_t nctas = (h->nlist + kCsThreads - 1) / kCsThreads;
+        if ((rc = h->coarse_mat.ensure(sizeof(uint64_t) * nq * nctas * kCsKeep))) return rc;
+        const size_t dsm = coarse_small_dist_smem(h->d);
+        if ((rc = set_smem(coarse_small_dist_kernel, dsm))) return rc;
+        dim3 grid((unsigned)nctas, (unsigned)((nq + kCsQ - 1) / kCsQ));
+        coarse_small_dist_kernel<<<grid, kCsThreads, dsm, st>>>(d_xq, h->cent, (int)nq, h->nlist, h->d,
+                                                               h->coarse_mat.as<uint64_t>());
+        LAUNCH_CHECK();
+        if (time_stages) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+        const int nkeys = (int)(nctas * kCsKeep);
+        const size_t ssm = sizeof(uint64_t) * std::max(nkeys, kThreads);
+        if ((rc = set_smem(coarse_small_select_kernel, ssm))) return rc;
+        coarse_small_select_kernel<<<(unsigned)nq, kThreads, ssm, st>>>(h->coarse_mat.as<uint64_t>(), nkeys, nprobe,
+                                                                       probe32, ids64, dis);
+        LAUNCH_CHECK();
+        return 0;
+    }
     if (tc_usable(h, nprobe)) {
         // tensor-core pre-filter + exact rescoring (coarse_tc.cuh)
         const int L = tc_candidates(h, nprobe);
@@ -347,7 +367,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     {
         const int64_t pairs = std::min<int64_t>(qb, nq) * nprobe;
         const int64_t target = 2 * (int64_t)h->num_sms;
-        if (pairs < target) nseg = (int)std::min<int64_t>(16, (target + pairs - 1) / pairs);
+        // as many segments as keep all work items in ONE wave of resident CTAs (two per SM)
+        if (pairs < target) nseg = (int)std::max<int64_t>(1, std::min<int64_t>(16, target / pairs));
         if (h->scan_variant >= 3) nseg = 1;   // forced multi-query kernels (tests): they scan whole lists
         if (h->force_nseg > 0) nseg = h->force_nseg;
     }
@@ -397,23 +418,32 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * kQuadScratchFloat4 * quad_ctas))) return rc;
 
         // pair setup
-        CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * h->nlist, st));
-        CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs * nseg, st));
-        fill_u32_kernel<<<grid1d(nqc, 256), 256, 0, st>>>(h->qthr.as<uint32_t>(), nqc, kInfBits);
-        LAUNCH_CHECK();
         PairStats* stats = h->stats.as<PairStats>();
-        pair_hist_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
-                                                             h->hist.as<int>(), stats);
-        LAUNCH_CHECK();
-        pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), h->nlist, gsz,
-                                             stats);
-        LAUNCH_CHECK();
-        CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, (gsz == 4 ? sizeof(QuadGroup) : sizeof(DuoGroup)) * npairs, st));
-        pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
-                                                                h->start.as<int>(), h->gstart.as<int>(),
-                                                                h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p,
-                                                                gsz);
-        LAUNCH_CHECK();
+        const bool small_setup = nseg > 1 && npairs <= 8192 && npairs * nseg <= (1 << 17) && !quad_ctas;
+        if (small_setup) {
+            // latency path: one kernel instead of two memsets and four kernels; pairs keep their natural order
+            pair_setup_small_kernel<<<1, 1024, 0, st>>>(probe32, (int)npairs, h->offsets.as<int64_t>(),
+                                                        h->order.as<int32_t>(), h->qthr.as<uint32_t>(), (int)nqc,
+                                                        h->out_cnt.as<int>(), (int)(npairs * nseg), stats);
+            LAUNCH_CHECK();
+        } else {
+            CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * h->nlist, st));
+            CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs * nseg, st));
+            fill_u32_kernel<<<grid1d(nqc, 256), 256, 0, st>>>(h->qthr.as<uint32_t>(), nqc, kInfBits);
+            LAUNCH_CHECK();
+            pair_hist_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
+                                                                 h->hist.as<int>(), stats);
+            LAUNCH_CHECK();
+            pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), h->nlist, gsz,
+                                                 stats);
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, (gsz == 4 ? sizeof(QuadGroup) : sizeof(DuoGroup)) * npairs, st));
+            pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
+                                                                    h->start.as<int>(), h->gstart.as<int>(),
+                                                                    h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p,
+                                                                    gsz);
+            LAUNCH_CHECK();
+        }
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));
 
         // K2+K3+K4

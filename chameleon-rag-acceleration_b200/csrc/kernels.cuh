@@ -261,6 +261,65 @@ __global__ void pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t n
     }
 }
 
+// Small batches (a few thousand pairs at most): nothing is gained by sorting the pairs by list, so the whole pair setup
+// is ONE single-CTA kernel: valid pairs are compacted in their natural order (stable), the per-query thresholds are
+// set to +inf, the per-slot candidate counts to zero, and the scan statistics are accumulated.
+__global__ void __launch_bounds__(1024) pair_setup_small_kernel(const int32_t* __restrict__ probe, int npairs,
+                                                                const int64_t* __restrict__ offsets,
+                                                                int32_t* __restrict__ order, uint32_t* __restrict__ qthr,
+                                                                int nq, int* __restrict__ out_cnt, int nslots,
+                                                                PairStats* __restrict__ stats) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    __shared__ unsigned long long total_codes;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        carry = 0;
+        total_codes = 0ull;
+    }
+    for (int i = tid; i < nq; i += 1024) qthr[i] = kInfBits;
+    for (int i = tid; i < nslots; i += 1024) out_cnt[i] = 0;
+    __syncthreads();
+    for (int base = 0; base < npairs; base += 1024) {
+        const int i = base + tid;
+        unsigned long long codes = 0ull;
+        if (i < npairs) {
+            const int l = probe[i];
+            if (l >= 0) {
+                const int64_t sz = offsets[l + 1] - offsets[l];
+                if (sz > 0) codes = static_cast<unsigned long long>(sz);
+            }
+        }
+        const bool valid = codes != 0ull;
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) warp_sums[wid] = __popc(bal);
+        unsigned long long csum = codes;
+        for (int o = 16; o > 0; o >>= 1) csum += __shfl_down_sync(0xffffffffu, csum, o);
+        if (lane == 0 && csum) atomicAdd(&total_codes, csum);
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;   // inclusive
+        }
+        __syncthreads();
+        const int pos = carry + (wid ? warp_sums[wid - 1] : 0) + __popc(bal & lanemask_lt());
+        if (valid) order[pos] = i;
+        __syncthreads();
+        if (tid == 0) carry += warp_sums[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        stats->nvalid = carry;
+        stats->ngroups = 0;
+        stats->work_counter = 0;
+        atomicAdd(&stats->scan_codes, total_codes);
+    }
+}
+
 __global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t v) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

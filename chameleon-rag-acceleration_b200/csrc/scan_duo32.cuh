@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kDuo32Threads, 1) scan_duo32_kernel(const Scan
                 if (nb == p.k) atomicMin(p.qthr + qb, static_cast<uint32_t>(s[p.k - 1] >> 32));
             }
         }
-        __syncthreads();
+        // no barrier here: the one at the top of the next item separates these reads from its first writes
     }
 }
 

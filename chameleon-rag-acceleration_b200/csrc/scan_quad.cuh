@@ -438,9 +438,12 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
             if (t0 + 1 < nblk) QUAD_ITER(c1, c3, 1)
             if (t0 + 2 < nblk) QUAD_ITER(c2, c0, 2)
             if (t0 + 3 < nblk) QUAD_ITER(c3, c1, 3)
-            // survivors of the next tile must fit: drain when more than one tile's worth is queued
-            const int seen = *reinterpret_cast<volatile int*>(&ctrl->nsurv[sphase]);
-            if (__syncthreads_or(seen > p.quad_drain_at)) drain();
+            // drain once enough survivors are waiting (tight thresholds early are worth more than fewer drains);
+            // the last tile goes straight to the final drain
+            if (t0 + kQuadTB < nblk) {
+                const int seen = *reinterpret_cast<volatile int*>(&ctrl->nsurv[sphase]);
+                if (__syncthreads_or(seen > p.quad_drain_at)) drain();
+            }
         }
 #undef QUAD_ITER
         __syncthreads();
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
                 }
             }
         }
-        __syncthreads();
+        // no barrier here: the one at the top of the next item separates these reads from its first writes
     }
 }
 

@@ -96,3 +96,22 @@ def test_tc_coarse_adversarial_near_ties(oracle, nlist):
     n = ctypes.c_int64()
     _lib.check(h.lib.b200_ivfpq_coarse_fallbacks(h.h, ctypes.byref(n)))
     assert n.value > 0, "near-duplicate centroids must trigger the exact fallback"
+
+
+@pytest.mark.parametrize("d,nlist,nq,nprobe", [(128, 8192, 1, 32), (768, 16384, 1, 32), (96, 1000, 5, 7), (20, 300, 16, 32),
+                                              (130, 4097, 9, 1), (128, 128, 3, 32)])
+def test_small_batch_coarse_identical_to_oracle(oracle, d, nlist, nq, nprobe):
+    """Latency path (coarse_small.cuh): exact distances + register top-32 per 128 centroids; must equal the oracle bit
+    for bit, duplicates (ties -> lower id) included."""
+    import b200ivfpq as faiss
+    rng = np.random.default_rng(d + nlist + nq)
+    cent = rng.random((nlist, d), dtype=np.float32)
+    cent[nlist // 2] = cent[3]                                   # an exact duplicate
+    xq = (cent[rng.integers(0, nlist, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * 0.1).astype(np.float32)
+    xq[0] = cent[3]                                              # distance 0 to both duplicates
+    dr, ir = oracle.C.coarse(xq, cent, nprobe)
+    idx = faiss.IndexFlatL2(d)
+    idx.add(cent)
+    D, I = idx.search(xq, nprobe)
+    _util.assert_bit_equal(I, ir, "probed ids (small batch)")
+    _util.assert_bit_equal(D, dr, "coarse distances (small batch)")
