@@ -105,7 +105,7 @@ struct b200_ivfpq_index {
     int64_t max_list = 0;   // longest inverted list
     int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
     // workspace
-    DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t, lutf, pq_maxnorm;
+    DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t, lutf, pq_maxnorm, lutg;
     DevBuf host_xq, host_D, host_I;
     // tensor-core coarse quantizer (K1): split-bf16 centroids, norms, per-call buffers
     DevBuf cent_bf16, cnorm, cmax2, q_bf16, qnorm, cand, cand_score, cand_cnt, flags, nflagged;
@@ -367,8 +367,9 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     {
         const int64_t pairs = std::min<int64_t>(qb, nq) * nprobe;
         const int64_t target = 2 * (int64_t)h->num_sms;
-        // as many segments as keep all work items in ONE wave of resident CTAs (two per SM)
-        if (pairs < target) nseg = (int)std::max<int64_t>(1, std::min<int64_t>(16, target / pairs));
+        // as many segments as keep all work items in ONE wave of resident CTAs (two per SM); at least two below one
+        // wave's worth of pairs (shorter critical path per CTA, the LUTs are prebuilt anyway)
+        if (pairs < target) nseg = (int)std::max<int64_t>(2, std::min<int64_t>(16, target / pairs));
         if (h->scan_variant >= 3) nseg = 1;   // forced multi-query kernels (tests): they scan whole lists
         if (h->force_nseg > 0) nseg = h->force_nseg;
     }
@@ -468,12 +469,22 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.nprobe = nprobe;
         sp.k = k;
         sp.nseg = nseg;
+        sp.lutg = nullptr;
         sp.negzero2 = 0x8000000080000000ull;
         {
             const char* v = getenv("B200_IVFPQ_QUAD_DRAIN");
             sp.quad_drain_at = v ? std::max(0, std::min(256, atoi(v))) : 256;
         }
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
+        if (nseg > 1 && npairs <= 1024) {
+            // small batches: every pair is scanned by nseg CTAs -- build its LUT once instead of nseg times
+            if ((rc = h->lutg.ensure(sizeof(float) * npairs * h->M * 256))) return rc;
+            dim3 lgrid((unsigned)npairs, (unsigned)((h->M + 7) / 8));
+            lut_small_kernel<<<lgrid, 256, 0, st>>>(xq, h->cent, h->pq, probe32, nprobe, h->d, h->M, h->dsub,
+                                                   use_skew ? 1 : 0, h->lutg.as<float>());
+            LAUNCH_CHECK();
+            sp.lutg = h->lutg.as<float>();
+        }
         if (h->scan_variant >= 2 && h->scan_variant != 4 && !use_skew &&
             !(h->scan_variant == 3 && duo32_supported(h->M, h->d, k)))
             return fail(B200_IVFPQ_EUNSUPPORTED, "skewed scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
@@ -581,7 +592,7 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
 int b200_ivfpq_destroy(b200_ivfpq_t h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t, &h->gstart, &h->groups, &h->lutf, &h->pq_maxnorm,
+    DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t, &h->gstart, &h->groups, &h->lutf, &h->pq_maxnorm, &h->lutg,
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
                       &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
                       &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged, &h->cand_cnt};

@@ -352,11 +352,40 @@ struct ScanParams {
     uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf
     PairStats* stats;
     int d, M, dsub, nprobe, k;
+    const float* lutg;        // small batches: LUTs built once per (query, probe) pair by lut_small_kernel, or nullptr.
+                              // Layout per pair: [c][m] (M == 16, the skewed kernel's store order) or [m][c]
     int quad_drain_at;        // scan_quad.cuh: survivors queued before the exact phase runs (<= 256)
     uint64_t negzero2;        // (-0.0f, -0.0f): an addend ptxas cannot see through (scan_duo.cuh lut_entry_duo)
     int nseg;                 // each (query, probe) pair is scanned by nseg CTAs (contiguous segments of its list):
                               // fills the GPU at small batch sizes; slot = pair * nseg + segment
 };
+
+// Small batches split every (query, probe) pair into nseg list segments, one CTA each; building the pair's LUT in each
+// of those CTAs multiplies the LUT work and the PQ-codebook traffic by nseg (C4 shape: 786 KB of codebook per CTA).
+// This kernel builds every pair's LUT ONCE: grid (pair, m-chunk of 8 sub-quantizers), thread = code value.
+//   T[m][c] = sum_j ((q - cent)[m*dsub+j] - pq[m][c][j])^2, j ascending, separately rounded (the oracle's form).
+__global__ void __launch_bounds__(256) lut_small_kernel(const float* __restrict__ xq, const float* __restrict__ cent,
+                                                        const float* __restrict__ pq, const int32_t* __restrict__ probe,
+                                                        int nprobe, int d, int M, int dsub, int cm_layout,
+                                                        float* __restrict__ lutg) {
+    const int pair = blockIdx.x, c = threadIdx.x;
+    const int list = probe[pair];
+    if (list < 0) return;
+    const int q = pair / nprobe;
+    const float* xr = xq + static_cast<int64_t>(q) * d;
+    const float* cr = cent + static_cast<int64_t>(list) * d;
+    float* out = lutg + static_cast<int64_t>(pair) * M * 256;
+    const int m0 = blockIdx.y * 8, m1 = min(M, m0 + 8);
+    for (int m = m0; m < m1; m++) {
+        const float* pc = pq + (static_cast<int64_t>(m) * 256 + c) * dsub;
+        float acc = 0.0f;
+        for (int j = 0; j < dsub; j++) {
+            const float r = __fsub_rn(__ldg(xr + m * dsub + j), __ldg(cr + m * dsub + j));
+            acc = sqdiff_acc(acc, r, __ldg(pc + j));
+        }
+        out[cm_layout ? c * M + m : m * 256 + c] = acc;
+    }
+}
 
 constexpr int kScanCap = 2048;
 constexpr int kScanUnroll = 4;
@@ -461,20 +490,27 @@ __global__ void __launch_bounds__(kThreads) scan_pairs_kernel(const ScanParams p
         }
         const int64_t n = min(seglen, ntot - soff);
 
-        // a2: residual
-        for (int j = tid; j < p.d; j += kThreads)
-            res[j] = __fsub_rn(p.xq[static_cast<int64_t>(q) * p.d + j], p.cent[static_cast<int64_t>(list) * p.d + j]);
         const uint32_t ext_thr = *reinterpret_cast<volatile uint32_t*>(p.qthr + q);
         if (tid == 0) tk.reset(ext_thr);
-        __syncthreads();
-        // a3: LUT
-        for (int idx = tid; idx < p.M * 256; idx += kThreads) {
-            const int m = idx >> 8;
-            const float* pc = p.pq + static_cast<int64_t>(idx) * p.dsub;
-            const float* r = res + m * p.dsub;
-            float acc = 0.0f;
-            for (int j = 0; j < p.dsub; j++) acc = sqdiff_acc(acc, r[j], __ldg(pc + j));
-            lut[idx] = acc;
+        if (p.lutg) {
+            // small batches: the pair's LUT was built once by lut_small_kernel ([m][c] layout)
+            const float4* src = reinterpret_cast<const float4*>(p.lutg + static_cast<int64_t>(pair) * p.M * 256);
+            float4* dst = reinterpret_cast<float4*>(lut);
+            for (int idx = tid; idx < p.M * 64; idx += kThreads) dst[idx] = src[idx];
+        } else {
+            // a2: residual
+            for (int j = tid; j < p.d; j += kThreads)
+                res[j] = __fsub_rn(p.xq[static_cast<int64_t>(q) * p.d + j], p.cent[static_cast<int64_t>(list) * p.d + j]);
+            __syncthreads();
+            // a3: LUT
+            for (int idx = tid; idx < p.M * 256; idx += kThreads) {
+                const int m = idx >> 8;
+                const float* pc = p.pq + static_cast<int64_t>(idx) * p.dsub;
+                const float* r = res + m * p.dsub;
+                float acc = 0.0f;
+                for (int j = 0; j < p.dsub; j++) acc = sqdiff_acc(acc, r[j], __ldg(pc + j));
+                lut[idx] = acc;
+            }
         }
         __syncthreads();
         // a4 + a5

@@ -194,11 +194,26 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
         uint4 c2 = skew_load_code16(lp, 256u + tid, n);           // code 1
         uint4 c3;
 
+        const uint32_t ext_thr = *reinterpret_cast<volatile uint32_t*>(p.qthr + q);
+        if (tid == 0) tk.reset(ext_thr);
+        if (p.lutg) {
+            // small batches: the pair's LUT was built once by lut_small_kernel, [c][m] layout (a half-warp reads the 16
+            // entries of one code value: 64 contiguous bytes); only the periodic copies are made here
+            const float* src = p.lutg + static_cast<int64_t>(pair) * (M * 256);
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int c = lc0 + 16 * i;
+                const float a = __ldg(src + c * M + lm);
+                float* row = lut + c * kSkewRowWords + lm;
+                row[copy0] = a;
+                row[copy0 ^ 16] = a;
+                row[32 + copy0] = a;
+                row[32 + (copy0 ^ 16)] = a;
+            }
+        } else {
         // a2: residual
         for (int j = tid; j < p.d; j += kThreads)
             res[j] = __fsub_rn(p.xq[static_cast<int64_t>(q) * p.d + j], p.cent[static_cast<int64_t>(list) * p.d + j]);
-        const uint32_t ext_thr = *reinterpret_cast<volatile uint32_t*>(p.qthr + q);
-        if (tid == 0) tk.reset(ext_thr);
         __syncthreads();
         // a3: LUT with periodic rows lut[c][w] = T[w % 16][c], w < 64
         if constexpr (DSUB != 0) {
@@ -228,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_skew16_kernel(const ScanPara
                 row[32 + copy0] = a;
                 row[32 + (copy0 ^ 16)] = a;
             }
+        }
         }
         __syncthreads();
 
