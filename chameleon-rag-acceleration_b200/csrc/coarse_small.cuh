@@ -51,39 +51,62 @@ coarse_small_dist_kernel(const float* __restrict__ xq, const float* __restrict__
     for (int q = 0; q < kCsQ; q++) acc[q] = 0.0f;
     const bool vec4 = (d & 3) == 0;
     const int64_t my_c = c0 + tid;
-    for (int j0 = 0; j0 < d; j0 += kCsJ) {
-        const int jn = min(kCsJ, d - j0);
-        __syncthreads();   // previous slice consumed (and, first time round, the queries staged)
-        if (vec4) {
-            const int c4 = (tid & 7) * 4, r0 = tid >> 3;
-            float4 v[kCsThreads / 16];
-#pragma unroll
-            for (int ps = 0; ps < kCsThreads / 16; ps++) {
-                const int64_t c = c0 + r0 + 16 * ps;
-                v[ps] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (c < nlist && c4 < jn) v[ps] = __ldg(reinterpret_cast<const float4*>(cent + c * d + j0 + c4));
-            }
-#pragma unroll
-            for (int ps = 0; ps < kCsThreads / 16; ps++) {
-                float* t = tile + (r0 + 16 * ps) * (kCsJ + 1) + c4;
-                t[0] = v[ps].x;
-                t[1] = v[ps].y;
-                t[2] = v[ps].z;
-                t[3] = v[ps].w;
-            }
-        } else {
+    const float* row = tile + tid * (kCsJ + 1);
+    if (vec4) {
+        // 8 threads x float4 cover one 128-byte row slice, 16 rows per pass; the loads of slice s + 2 are issued before
+        // slice s is consumed (two register buffers), so the cold-memory latency overlaps the arithmetic
+        const int c4 = (tid & 7) * 4, r0 = tid >> 3;
+        const int nsl = (d + kCsJ - 1) / kCsJ;
+        float4 va[kCsThreads / 16], vb[kCsThreads / 16];
+#define CS_LOAD(V, S)                                                                                     \
+    _Pragma("unroll") for (int ps = 0; ps < kCsThreads / 16; ps++) {                                      \
+        const int64_t c = c0 + r0 + 16 * ps;                                                              \
+        V[ps] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);                                                      \
+        if ((S) < nsl && c < nlist && (S) * kCsJ + c4 < d)                                                \
+            V[ps] = __ldg(reinterpret_cast<const float4*>(cent + c * d + (S) * kCsJ + c4));               \
+    }
+#define CS_CONSUME(V, S)                                                                                  \
+    {                                                                                                     \
+        __syncthreads(); /* previous slice consumed (first time round: the queries are staged) */         \
+        _Pragma("unroll") for (int ps = 0; ps < kCsThreads / 16; ps++) {                                  \
+            float* t = tile + (r0 + 16 * ps) * (kCsJ + 1) + c4;                                           \
+            t[0] = V[ps].x;                                                                               \
+            t[1] = V[ps].y;                                                                               \
+            t[2] = V[ps].z;                                                                               \
+            t[3] = V[ps].w;                                                                               \
+        }                                                                                                 \
+        __syncthreads();                                                                                  \
+        CS_LOAD(V, (S) + 2)                                                                               \
+        const int j0 = (S) * kCsJ, jn = min(kCsJ, d - j0);                                                \
+        for (int jj = 0; jj < jn; jj++) {                                                                 \
+            const float x = row[jj];                                                                      \
+            _Pragma("unroll") for (int q = 0; q < kCsQ; q++)                                              \
+                if (q < nqc) acc[q] = sqdiff_acc(acc[q], sq[q * dpad + j0 + jj], x);                      \
+        }                                                                                                 \
+    }
+        CS_LOAD(va, 0)
+        CS_LOAD(vb, 1)
+        for (int s = 0; s < nsl; s += 2) {
+            CS_CONSUME(va, s)
+            if (s + 1 < nsl) CS_CONSUME(vb, s + 1)
+        }
+#undef CS_LOAD
+#undef CS_CONSUME
+    } else {
+        for (int j0 = 0; j0 < d; j0 += kCsJ) {
+            const int jn = min(kCsJ, d - j0);
+            __syncthreads();
             for (int i = warp; i < kCsThreads; i += kCsThreads / 32) {
                 const int64_t c = c0 + i;
                 if (lane < jn) tile[i * (kCsJ + 1) + lane] = c < nlist ? __ldg(cent + c * d + j0 + lane) : 0.0f;
             }
-        }
-        __syncthreads();
-        const float* row = tile + tid * (kCsJ + 1);
-        for (int jj = 0; jj < jn; jj++) {
-            const float x = row[jj];
+            __syncthreads();
+            for (int jj = 0; jj < jn; jj++) {
+                const float x = row[jj];
 #pragma unroll
-            for (int q = 0; q < kCsQ; q++)
-                if (q < nqc) acc[q] = sqdiff_acc(acc[q], sq[q * dpad + j0 + jj], x);
+                for (int q = 0; q < kCsQ; q++)
+                    if (q < nqc) acc[q] = sqdiff_acc(acc[q], sq[q * dpad + j0 + jj], x);
+            }
         }
     }
     // the CTA's 32 smallest keys per query: sort each warp's 32, merge the four runs
