@@ -13,7 +13,7 @@ import re
 from .index import METRIC_L2, IndexFlatL2, IndexIVFPQ
 
 _IVFPQ = re.compile(r"^IVF(\d+),PQ(\d+)(?:x(\d+))?$")
-_OPQ = re.compile(r"^OPQ\d+(_\d+)?,")
+_OPQ = re.compile(r"^OPQ(\d+)(?:_(\d+))?,(.*)$")
 
 
 def index_factory(d: int, description: str, metric: int = METRIC_L2):
@@ -22,9 +22,17 @@ def index_factory(d: int, description: str, metric: int = METRIC_L2):
         raise RuntimeError("index_factory: only METRIC_L2 is supported")
     if key == "Flat":
         return IndexFlatL2(d)
-    if _OPQ.match(key):
-        raise RuntimeError(f"index_factory: '{key}': the OPQ pre-transform is outside the hot-path scope "
-                           "(SURVEY.md section 8f, rank 3)")
+    o = _OPQ.match(key)
+    if o:
+        # "OPQ16,IVF4096,PQ16" / "OPQ16_64,..." (bench_cpu_recall.py:54): rotation (+ reduction to 64 dims) in front
+        from .transforms import IndexPreTransform, OPQMatrix
+        vt = OPQMatrix(d, int(o.group(1)), int(o.group(2)) if o.group(2) else -1)
+        sub = index_factory(vt.d_out, o.group(3), metric)
+        if not isinstance(sub, IndexIVFPQ):
+            raise RuntimeError(f"index_factory: '{key}': OPQ is supported in front of IVF<nlist>,PQ<m> only")
+        if sub.pq.M != vt.M:
+            raise RuntimeError(f"index_factory: '{key}': OPQ{vt.M} does not match PQ{sub.pq.M}")
+        return IndexPreTransform(vt, sub)
     m = _IVFPQ.match(key)
     if not m:
         raise RuntimeError(f"index_factory: could not parse '{key}' (supported: 'Flat', 'IVF<nlist>,PQ<m>[x8]')")
@@ -43,6 +51,7 @@ class ParameterSpace:
     def _set(index, name: str, value: float):
         if name != "nprobe":
             raise RuntimeError(f"ParameterSpace: could not set parameter {name}")
+        index = getattr(index, "index", index)          # IndexPreTransform -> its IVF sub-index
         v = int(round(float(value)))
         if v < 1:
             raise RuntimeError("nprobe must be >= 1")

@@ -62,15 +62,17 @@ def kmeans(x: torch.Tensor, k: int, niter: int = 25, seed: int = 1234, max_point
     return c.contiguous()
 
 
-def kmeans_subspaces(x: torch.Tensor, M: int, ksub: int = 256, niter: int = 25, seed: int = 1234) -> torch.Tensor:
-    """Per-subspace k-means for the product quantizer.  x: (n, d) residuals; returns (M, ksub, dsub)."""
+def kmeans_subspaces(x: torch.Tensor, M: int, ksub: int = 256, niter: int = 25, seed: int = 1234,
+                     init: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-subspace k-means for the product quantizer.  x: (n, d) residuals; returns (M, ksub, dsub).
+    `init` (M, ksub, dsub) warm-starts the centroids (OPQ retrains the PQ a few iterations per rotation update)."""
     n, d = x.shape
     dsub = d // M
     xs = x.reshape(n, M, dsub).permute(1, 0, 2).contiguous()          # (M, n, dsub)
     g = torch.Generator(device=x.device)
     g.manual_seed(seed)
     perm = torch.randperm(n, generator=g, device=x.device)[:ksub]
-    c = xs[:, perm, :].clone()                                          # (M, ksub, dsub)
+    c = xs[:, perm, :].clone() if init is None else init.clone()        # (M, ksub, dsub)
     ar = torch.arange(M, device=x.device).unsqueeze(1)
     for _ in range(niter):
         cn = (c * c).sum(2)                                             # (M, ksub)

@@ -83,7 +83,16 @@ def test_index_factory_grammar():
         assert idx.pq.dsub == d // m and idx.pq.ksub == 256 and idx.pq.code_size == m
         assert not idx.is_trained
     assert isinstance(faiss.index_factory(64, "Flat"), faiss.IndexFlatL2)
-    for bad in ["IVF1024,PQ16x4", "OPQ16,IVF1024,PQ16", "IVF1024,Flat", "IMI2x8,PQ16", "IVF,PQ16", "garbage"]:
+    opq = faiss.index_factory(128, "OPQ16,IVF1024,PQ16")          # bench_cpu_recall.py:54
+    assert isinstance(opq, faiss.IndexPreTransform) and isinstance(opq.index, faiss.IndexIVFPQ)
+    assert (opq.d, opq.index.d, opq.chain.size(), opq.chain.at(0).d_out, opq.is_trained) == (128, 128, 1, 128, False)
+    opq64 = faiss.index_factory(128, "OPQ16_64,IVF256,PQ16")
+    assert (opq64.d, opq64.index.d, opq64.index.pq.dsub) == (128, 64, 4)
+    ps = faiss.ParameterSpace()
+    ps.set_index_parameters(opq, "nprobe=12")
+    assert opq.nprobe == 12 and opq.index.nprobe == 12
+    for bad in ["IVF1024,PQ16x4", "OPQ8,IVF1024,PQ16", "OPQ16,IVF1024,Flat", "IVF1024,Flat", "IMI2x8,PQ16", "IVF,PQ16",
+                "garbage"]:
         with pytest.raises(RuntimeError):
             faiss.index_factory(128, bad)
     with pytest.raises(RuntimeError):
