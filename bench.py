@@ -461,6 +461,11 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32/u8", "data": "synthetic",
             "config": {"workload": workload_name(cfg, args), "sharding": f"by vector: 2M-vector chunks round-robin over {world} GPU(s)",
+                       "shard_merge": ("none" if world == 1 else
+                                       "K5 reads every shard's top-k in place over NVLink (symmetric memory)"
+                                       if getattr(searcher, "peer_merge", False) else
+                                       "NCCL all-gather + K5" + (f" (peer memory unavailable: {searcher.peer_merge_error})"
+                                                                 if getattr(searcher, "peer_merge_error", None) else "")),
                        "l2_policy": "inputs larger than L2 (codes %.0f MB per GPU vs 126 MB L2)" %
                                     (index.ntotal * M / 1e6),
                        "scan_kernel": os.environ.get("B200_IVFPQ_SCAN", "auto"), "ntotal_per_gpu": index.ntotal,

@@ -51,6 +51,16 @@ def _as_f32_matrix(x, d: int, what: str):
     return np.ascontiguousarray(x)
 
 
+def _check_out(out, nq: int, k: int, dev):
+    D, I = out
+    ok = (isinstance(D, torch.Tensor) and isinstance(I, torch.Tensor) and D.is_cuda and I.is_cuda and
+          D.dtype == torch.float32 and I.dtype == torch.int64 and tuple(D.shape) == (nq, k) and
+          tuple(I.shape) == (nq, k) and D.is_contiguous() and I.is_contiguous() and D.device == dev and I.device == dev)
+    if not ok:
+        raise AssertionError("out = (D, I) must be contiguous CUDA tensors (nq, k) f32 / i64 on the index's device")
+    return D, I
+
+
 def _to_device(x, device) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device, non_blocking=True).contiguous()
@@ -422,8 +432,10 @@ class IndexIVFPQ:
         if not (1 <= nprobe <= MAX_NPROBE):
             raise RuntimeError(f"nprobe = {nprobe} out of [1, {MAX_NPROBE}]")
 
-    def search(self, x, k: int):
-        """index.search(xq, k) -> (D, I), rows ascending by distance, unfilled slots I = -1 / D = FLT_MAX."""
+    def search(self, x, k: int, out=None):
+        """index.search(xq, k) -> (D, I), rows ascending by distance, unfilled slots I = -1 / D = FLT_MAX.
+        out = (D, I): preallocated CUDA tensors to write into (torch input only; used by the multi-GPU layer to have
+        the results land directly in peer-visible memory)."""
         x = _as_f32_matrix(x, self.d, "search")
         nprobe = int(self.nprobe)
         self._check_search(k, nprobe)
@@ -433,8 +445,11 @@ class IndexIVFPQ:
         with torch.cuda.device(dev):
             if isinstance(x, torch.Tensor):
                 xq = x.to(dev).contiguous()
-                D = torch.empty((nq, k), dtype=torch.float32, device=dev)
-                I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                if out is not None:
+                    D, I = _check_out(out, nq, k, dev)
+                else:
+                    D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+                    I = torch.empty((nq, k), dtype=torch.int64, device=dev)
                 _lib.check(h.lib.b200_ivfpq_search(h.h, nq, xq.data_ptr(), k, nprobe, D.data_ptr(), I.data_ptr(),
                                                    _stream_ptr(dev)))
                 return D, I
@@ -443,7 +458,7 @@ class IndexIVFPQ:
             _lib.check(h.lib.b200_ivfpq_search_host(h.h, nq, x.ctypes.data, k, nprobe, D.ctypes.data, I.ctypes.data))
             return D, I
 
-    def search_preassigned(self, x, k: int, list_ids):
+    def search_preassigned(self, x, k: int, list_ids, out=None):
         """faiss.contrib.ivf_tools.search_preassigned(index, xq, k, list_ids) (faiss_server.py:233)."""
         x = _as_f32_matrix(x, self.d, "search_preassigned")
         is_torch = isinstance(x, torch.Tensor)
@@ -459,8 +474,11 @@ class IndexIVFPQ:
         self._check_search(k, nprobe)
         h = self._sync_lists()
         xq = _to_device(x, dev)
-        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if out is not None and is_torch:
+            D, I = _check_out(out, nq, k, dev)
+        else:
+            D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            I = torch.empty((nq, k), dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             _lib.check(h.lib.b200_ivfpq_search_preassigned(h.h, nq, xq.data_ptr(), k, nprobe, lids.data_ptr(),
                                                            D.data_ptr(), I.data_ptr(), _stream_ptr(dev)))

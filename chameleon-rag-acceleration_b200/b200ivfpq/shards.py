@@ -13,6 +13,7 @@ every rank.  No other collective exists on the path.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -92,7 +93,7 @@ class DistributedIndexIVFPQ:
     `merge_fn` / `local_search_fn` are injection points for the CPU (gloo) tests of the exchange logic; the
     product path uses the CUDA kernels."""
 
-    def __init__(self, local_index, group=None, merge_fn=None, local_search_fn=None, shard_coarse=True):
+    def __init__(self, local_index, group=None, merge_fn=None, local_search_fn=None, shard_coarse=True, peer_merge=None):
         import torch.distributed as dist
         self.dist = dist
         self.local = local_index
@@ -103,6 +104,14 @@ class DistributedIndexIVFPQ:
         self._injected_search = local_search_fn
         self.shard_coarse = shard_coarse
         self.d = getattr(local_index, "d", None)
+        # Peer-memory merge: every rank's (D, I) lands in a symmetric-memory buffer that all GPUs of the box map into
+        # their address space; K5 then reads the shards in place over NVLink / NVSwitch -- no all-gather, no staging
+        # copies.  Falls back to the NCCL all-gather when symmetric memory cannot be set up (or B200_IVFPQ_P2P=0).
+        if peer_merge is None:
+            peer_merge = os.environ.get("B200_IVFPQ_P2P", "1") != "0"
+        self.peer_merge = bool(peer_merge) and merge_fn is None and local_search_fn is None and self.world > 1
+        self._symm = None          # (buffer, handle, capacity in result slots)
+        self.peer_merge_error = None
 
     @property
     def nprobe(self):
@@ -123,20 +132,63 @@ class DistributedIndexIVFPQ:
         out = out.view((self.world, hmax) + mine.shape[1:])
         return torch.cat([out[r, :counts[r]] for r in range(self.world)], 0)
 
-    def _local_search(self, xq: torch.Tensor, k: int):
+    def _local_search(self, xq: torch.Tensor, k: int, out=None):
         if self._injected_search is not None:
             return self._injected_search(xq, k)
         nq, nprobe = xq.shape[0], int(self.local.nprobe)
         if not (self.shard_coarse and self.world > 1 and nq >= 8 * self.world):
-            return self.local.search(xq, k)
+            return self.local.search(xq, k, out=out) if out is not None else self.local.search(xq, k)
         # coarse stage on my slice of the queries, then exchange the probe lists
         bounds = [(nq * r) // self.world for r in range(self.world + 1)]
         counts = [bounds[r + 1] - bounds[r] for r in range(self.world)]
         _, ids = self.local.quantizer.search(xq[bounds[self.rank]:bounds[self.rank + 1]], min(nprobe, self.local.nlist))
         probes = self._all_gather_rows(ids, counts)
+        if out is not None:
+            return self.local.search_preassigned(xq, k, probes, out=out)
         return self.local.search_preassigned(xq, k, probes)
 
+    # ---- peer-memory path --------------------------------------------------------------------------------
+    def _symm_setup(self, slots: int):
+        """(Re)allocate the symmetric result buffer for `slots` (= nq * k) results.  Collective: every rank calls it
+        with the same size because every rank searches the same batch."""
+        import torch.distributed._symmetric_memory as symm
+        dev = torch.device("cuda", torch.cuda.current_device())
+        cap = max(1 << 16, 1 << (int(slots) - 1).bit_length())
+        group = self.group if self.group is not None else self.dist.group.WORLD
+        buf = symm.empty((cap * 12 + 256,), dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(buf, group)
+        self._symm = (buf, hdl, cap)
+
+    def _search_peer(self, xq: torch.Tensor, k: int):
+        nq = xq.shape[0]
+        slots = nq * k
+        if self._symm is None or self._symm[2] < slots:
+            self._symm_setup(slots)
+        buf, hdl, cap = self._symm
+        d_off, i_off = 0, ((cap * 4 + 255) // 256) * 256
+        D_loc = buf[d_off:d_off + slots * 4].view(torch.float32).view(nq, k)
+        I_loc = buf[i_off:i_off + slots * 8].view(torch.int64).view(nq, k)
+        self._local_search(xq, k, out=(D_loc, I_loc))
+        hdl.barrier(channel=0)                       # every shard's results are in place (device-side, no host sync)
+        D = torch.empty((nq, k), dtype=torch.float32, device=xq.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=xq.device)
+        lib = _lib.load()
+        with torch.cuda.device(xq.device):
+            st = int(torch.cuda.current_stream(xq.device).cuda_stream)
+            _lib.check(lib.b200_ivfpq_merge_shards_peer(self.world, nq, k, int(hdl.buffer_ptrs_dev), d_off, i_off,
+                                                        D.data_ptr(), I.data_ptr(), st))
+        hdl.barrier(channel=1)                       # nobody overwrites its buffer while a peer still reads it
+        return D, I
+
     def search(self, xq: torch.Tensor, k: int):
+        if self.peer_merge and isinstance(xq, torch.Tensor) and xq.is_cuda:
+            try:
+                return self._search_peer(xq, k)
+            except Exception as e:   # symmetric memory unavailable on this system: use the NCCL path from now on
+                if self._symm is not None:
+                    raise
+                self.peer_merge = False
+                self.peer_merge_error = f"{type(e).__name__}: {e}"
         D, I = self._local_search(xq, k)
         if self.world == 1:
             return D, I

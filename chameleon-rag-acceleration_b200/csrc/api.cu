@@ -877,6 +877,24 @@ int b200_ivfpq_merge_shards(int nshard, int64_t nq, int k, const float* d_Ds, co
     return 0;
 }
 
+int b200_ivfpq_merge_shards_peer(int nshard, int64_t nq, int k, const void* const* d_bufs, int64_t d_off, int64_t i_off,
+                                 float* d_D, int64_t* d_I, void* stream) {
+    if (nshard < 1 || nq < 0) return fail(B200_IVFPQ_EINVAL, "bad nshard / nq");
+    if (k < 1 || k > B200_IVFPQ_MAX_K) return fail(B200_IVFPQ_EINVAL, "k = %d out of [1, %d]", k, B200_IVFPQ_MAX_K);
+    if ((int64_t)nshard * k >= (int64_t(1) << 31)) return fail(B200_IVFPQ_EINVAL, "nshard * k too large");
+    if (nq == 0) return 0;
+    if (!d_bufs || !d_D || !d_I || d_off < 0 || i_off < 0 || (d_off & 3) || (i_off & 7))
+        return fail(B200_IVFPQ_EINVAL, "null pointer or misaligned offset");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    size_t smem = TopK::smem_bytes(k, kMergeCap);
+    int rc = set_smem(merge_shards_peer_kernel, smem);
+    if (rc) return rc;
+    merge_shards_peer_kernel<<<(unsigned)nq, kThreads, smem, st>>>(
+        reinterpret_cast<const unsigned char* const*>(d_bufs), d_off, i_off, nshard, nq, k, d_D, d_I);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int b200_ivfpq_set_stage_timing(b200_ivfpq_t h, int enable) {
     if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
     h->timing = enable != 0;

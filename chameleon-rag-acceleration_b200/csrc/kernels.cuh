@@ -657,6 +657,57 @@ __global__ void __launch_bounds__(kThreads) merge_shards_kernel(const float* __r
     }
 }
 
+// K5 over peer memory: the same merge, but every shard's (D, I) is read in place from the GPU that produced it --
+// bufs[s] is rank s's result buffer mapped into this GPU's address space (NVLink / NVSwitch peer access), D at byte
+// offset d_off and I at i_off.  Replaces "NCCL all-gather into a staging tensor, unpack, merge" by one kernel whose
+// loads ARE the exchange (nq * k * 12 bytes per peer).  The caller brackets it with the symmetric-memory barriers.
+__global__ void __launch_bounds__(kThreads) merge_shards_peer_kernel(const unsigned char* const* __restrict__ bufs,
+                                                                     int64_t d_off, int64_t i_off, int nshard,
+                                                                     int64_t nq, int k, float* __restrict__ D,
+                                                                     int64_t* __restrict__ I) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TopK tk;
+    tk.bind(smem_raw, k, kMergeCap);
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    if (tid == 0) tk.reset(kInfBits);
+    __syncthreads();
+    uint32_t thr = kInfBits;
+    const int64_t total = static_cast<int64_t>(nshard) * k;
+    for (int64_t base = 0; base < total; base += kMergeTile) {
+#pragma unroll
+        for (int u = 0; u < kMergeTile / kThreads; u++) {
+            int64_t c = base + u * kThreads + tid;
+            uint32_t bits = 0xffffffffu;
+            if (c < total) {
+                const int64_t s = c / k, j = c % k;
+                const int64_t* Is = reinterpret_cast<const int64_t*>(bufs[s] + i_off);
+                const float* Ds = reinterpret_cast<const float*>(bufs[s] + d_off);
+                if (__ldcv(Is + q * k + j) >= 0) bits = __float_as_uint(__ldcv(Ds + q * k + j));
+            }
+            tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
+        }
+        tk.sync_and_flush_if_over<kThreads>(kMergeCap - kMergeTile, kInfBits);
+        thr = tk.threshold();
+    }
+    __syncthreads();
+    tk.flush<kThreads>(kInfBits);
+    const int nb = tk.count();
+    const uint64_t* s = tk.sorted();
+    for (int i = tid; i < k; i += kThreads) {
+        float dv = FLT_MAX;
+        int64_t id = -1;
+        if (i < nb) {
+            const uint32_t tag = static_cast<uint32_t>(s[i] & 0xffffffffu);
+            const int64_t sh = tag / k, j = tag % k;
+            id = __ldcv(reinterpret_cast<const int64_t*>(bufs[sh] + i_off) + q * k + j);
+            dv = __ldcv(reinterpret_cast<const float*>(bufs[sh] + d_off) + q * k + j);
+        }
+        D[q * k + i] = dv;
+        I[q * k + i] = id;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // a9: PQ encode of residuals for index.add.  grid = (ceil(n / 256), M); each CTA stages pq[m] in
 // shared memory, each thread encodes sub-vector m of one vector: argmin_k sum_j ((x-c)_j - pq[m][k][j])^2,

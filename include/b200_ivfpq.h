@@ -114,6 +114,14 @@ B200_API int b200_ivfpq_assign_encode(b200_ivfpq_t h, int64_t n, const float* d_
 B200_API int b200_ivfpq_merge_shards(int nshard, int64_t nq, int k, const float* d_Ds, const int64_t* d_Is, float* d_D,
                             int64_t* d_I, void* stream);
 
+/* The same merge over PEER MEMORY: d_bufs is a DEVICE array of nshard base pointers, entry s being rank s's result
+ * buffer mapped into this GPU's address space (CUDA peer access over NVLink / NVSwitch, e.g. torch symmetric memory's
+ * buffer_ptrs_dev); every buffer holds D (nq, k) f32 at byte offset d_off and I (nq, k) i64 at i_off.  The kernel's
+ * loads are the exchange: no all-gather, no staging copy.  The caller orders it against the producers (a
+ * symmetric-memory barrier before, and one after before the buffers are overwritten). */
+B200_API int b200_ivfpq_merge_shards_peer(int nshard, int64_t nq, int k, const void* const* d_bufs, int64_t d_off,
+                                 int64_t i_off, float* d_D, int64_t* d_I, void* stream);
+
 /* instrumentation for bench.py / ncu: device time (ms, CUDA events on `stream`) the last search spent in
  * each stage: [0] coarse distances, [1] coarse select, [2] pair setup, [3] LUT+scan+top-k, [4] merge.
  * Timing is off by default; enabling it adds event records but no synchronisation to the search call
