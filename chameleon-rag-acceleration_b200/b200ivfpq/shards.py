@@ -111,6 +111,7 @@ class DistributedIndexIVFPQ:
             peer_merge = os.environ.get("B200_IVFPQ_P2P", "1") != "0"
         self.peer_merge = bool(peer_merge) and merge_fn is None and local_search_fn is None and self.world > 1
         self._symm = None          # (buffer, handle, capacity in result slots)
+        self._readers_pending = False   # peers may still be reading my buffer (previous search's merge)
         self.peer_merge_error = None
 
     @property
@@ -155,6 +156,9 @@ class DistributedIndexIVFPQ:
         dev = torch.device("cuda", torch.cuda.current_device())
         cap = max(1 << 16, 1 << (int(slots) - 1).bit_length())
         group = self.group if self.group is not None else self.dist.group.WORLD
+        if self._symm is not None and self._readers_pending:
+            self._symm[1].barrier(channel=1)          # peers are done with the old buffer before it is dropped
+            self._readers_pending = False
         buf = symm.empty((cap * 12 + 256,), dtype=torch.uint8, device=dev)
         hdl = symm.rendezvous(buf, group)
         self._symm = (buf, hdl, cap)
@@ -168,6 +172,11 @@ class DistributedIndexIVFPQ:
         d_off, i_off = 0, ((cap * 4 + 255) // 256) * 256
         D_loc = buf[d_off:d_off + slots * 4].view(torch.float32).view(nq, k)
         I_loc = buf[i_off:i_off + slots * 8].view(torch.int64).view(nq, k)
+        if self._readers_pending:
+            # nobody overwrites its buffer while a peer still reads it.  Enqueued here, i.e. in front of this search's
+            # own milliseconds of scanning, the wait is over long before it matters
+            hdl.barrier(channel=1)
+            self._readers_pending = False
         self._local_search(xq, k, out=(D_loc, I_loc))
         hdl.barrier(channel=0)                       # every shard's results are in place (device-side, no host sync)
         D = torch.empty((nq, k), dtype=torch.float32, device=xq.device)
@@ -177,7 +186,7 @@ class DistributedIndexIVFPQ:
             st = int(torch.cuda.current_stream(xq.device).cuda_stream)
             _lib.check(lib.b200_ivfpq_merge_shards_peer(self.world, nq, k, int(hdl.buffer_ptrs_dev), d_off, i_off,
                                                         D.data_ptr(), I.data_ptr(), st))
-        hdl.barrier(channel=1)                       # nobody overwrites its buffer while a peer still reads it
+        self._readers_pending = True
         return D, I
 
     def search(self, xq: torch.Tensor, k: int):

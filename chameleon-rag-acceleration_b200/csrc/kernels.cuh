@@ -683,7 +683,10 @@ __global__ void __launch_bounds__(kThreads) merge_shards_peer_kernel(const unsig
                 const int64_t s = c / k, j = c % k;
                 const int64_t* Is = reinterpret_cast<const int64_t*>(bufs[s] + i_off);
                 const float* Ds = reinterpret_cast<const float*>(bufs[s] + d_off);
-                if (__ldcv(Is + q * k + j) >= 0) bits = __float_as_uint(__ldcv(Ds + q * k + j));
+                // both remote loads are issued together (one NVLink round trip, not two)
+                const int64_t id = __ldcv(Is + q * k + j);
+                const float dv = __ldcv(Ds + q * k + j);
+                if (id >= 0) bits = __float_as_uint(dv);
             }
             tk.push(bits <= thr, make_key(bits, static_cast<uint32_t>(c)));
         }
