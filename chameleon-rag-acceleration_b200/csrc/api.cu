@@ -488,9 +488,12 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if (h->scan_variant >= 2 && h->scan_variant != 4 && !use_skew &&
             !(h->scan_variant == 3 && duo32_supported(h->M, h->d, k)))
             return fail(B200_IVFPQ_EUNSUPPORTED, "skewed scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
-        // two queries per work item pay off once lists are shared: on average >= 3 probing queries per list
+        // two queries per work item pay off once lists are shared.  With Poisson-distributed queries per list, one
+        // probing query per list on average already fills 70 % of the slots (4.8 x 0.7 > the one-query kernel's
+        // 2.9 TB/s); for M = 32, whose only alternative is the bank-conflicted generic kernel (2.1 TB/s), even
+        // half-empty work items win (C5 sweep: profiles/r1_sweep_c5_batch_nprobe.json)
         bool use_duo = use_skew && nseg == 1 && h->scan_variant != 2 &&
-                       (h->scan_variant == 3 || npairs >= 3 * h->nlist);
+                       (h->scan_variant == 3 || npairs >= h->nlist);
         if (quad_ctas) {
             if ((rc = launch_scan_quad(sp, h->pq_t.as<float>(), quad_ctas, st)))
                 return fail(B200_IVFPQ_ECUDA, "four-query scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -503,7 +506,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             }
             g_launches.fetch_add(1);
         } else if (duo32_supported(h->M, h->d, k) && aligned16 && nseg == 1 && h->scan_variant != 1 &&
-                   h->scan_variant != 2 && (h->scan_variant == 3 || npairs >= 3 * h->nlist) &&
+                   h->scan_variant != 2 && (h->scan_variant == 3 || 2 * npairs >= h->nlist) &&
                    (rc = launch_scan_duo32(sp, h->pq_t.as<float>(), npairs, h->num_sms, st)) != -2) {
             // M = 32: two queries per work item, two alternating tables (scan_duo32.cuh)
             if (rc == -1) return fail(B200_IVFPQ_ECUDA, "two-query M=32 scan launch failed: %s",
