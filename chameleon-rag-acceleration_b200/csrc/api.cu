@@ -412,11 +412,11 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if (quad_supported(h->M, h->d, k) && aligned16 && nseg == 1 && h->max_list < (int64_t)kQuadMaxList &&
             (h->scan_variant == 4 ||
              (h->scan_variant == 0 && npairs >= 6 * h->nlist && h->ntotal >= kQuadMinAvgList * h->nlist)))
-            quad_ctas = quad_grid(h->dsub, h->d, k, npairs, h->num_sms);
+            quad_ctas = quad_grid(h->M, h->dsub, h->d, k, npairs, h->num_sms);
         if (h->scan_variant == 4 && quad_ctas == 0)
             return fail(B200_IVFPQ_EUNSUPPORTED, "four-query scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
         const int gsz = quad_ctas ? 4 : 2;
-        if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * kQuadScratchFloat4 * quad_ctas))) return rc;
+        if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * quad_scratch_float4(h->M) * quad_ctas))) return rc;
 
         // pair setup
         PairStats* stats = h->stats.as<PairStats>();

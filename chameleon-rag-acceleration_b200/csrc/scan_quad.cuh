@@ -32,34 +32,48 @@
 
 namespace b200 {
 
-constexpr int kQuadLutBytes = 256 * 256;          // 256 code values x 32 periodic entries x 4 x u16
-constexpr int kQuadCap = 1024;                    // exact-candidate queue per query
+constexpr int kQuadLutBytes = 256 * 256;          // one table: 256 code values x 32 periodic entries x 4 x u16
+constexpr int kQuadCap = 1024;                    // exact-candidate queue per query (M = 16)
 constexpr int kQuadSurvMin = 1280;                // survivor queue (u32 each): one tile of 1024 codes + the drain trigger
 constexpr int kQuadSurvMax = 1280;
-constexpr int kQuadTB = 4;                        // blocks (of 32 codes) per warp per tile
 constexpr uint32_t kQuadMaxList = 1u << 28;       // survivor entry = (offset << 4) | query mask
-constexpr size_t kQuadScratchFloat4 = 16 * 256;   // exact LUT of one CTA in global memory: [m][c] float4
+
+// M = 16: 256 threads, two CTAs per SM, one table.  M = 32: the 32-byte code is two independent 16-byte halves (integer
+// sums do not care about the order), each with its own table: 512 threads, one CTA per SM, entries quantised to 10
+// bits so that 32 of them still sum below 2^15.
+template <int M>
+struct QuadCfg {
+    static_assert(M == 16 || M == 32, "M = 16 or 32");
+    static constexpr int kT = 16 * M;                       // threads per CTA
+    static constexpr int kTables = M / 16;
+    static constexpr int kCtasPerSm = M == 16 ? 2 : 1;
+    static constexpr uint32_t kQMax = M == 16 ? 2047u : 1023u;
+    static constexpr int kCap = M == 16 ? kQuadCap : 2048;  // candidate queue per query
+    static constexpr int kTileBlocks = 1024 / kT;           // blocks of kT codes between survivor checks
+    static constexpr size_t kScratchFloat4 = static_cast<size_t>(M) * 256;   // exact LUT of one CTA: [m][c] float4
+};
+inline size_t quad_scratch_float4(int M) { return static_cast<size_t>(M) * 256; }
 
 inline bool quad_supported(int M, int d, int k) {
     (void)d;
-    return M == 16 && k <= 512;
+    return (M == 16 || M == 32) && k <= 512;
 }
 
 // shared memory: [ lut16 | residuals (4 x dpad f32) | 4 x TopK | survivors | control ]
-__host__ __device__ inline size_t quad_smem_fixed(int d, int k) {
-    return kQuadLutBytes + 4 * sizeof(float) * static_cast<size_t>((d + 3) & ~3) + 4 * TopK::smem_bytes(k, kQuadCap) + 64 +
-           2 * sizeof(QuadGroup);
+__host__ __device__ inline size_t quad_smem_fixed(int M, int d, int k) {
+    return static_cast<size_t>(M / 16) * kQuadLutBytes + 4 * sizeof(float) * static_cast<size_t>((d + 3) & ~3) +
+           4 * TopK::smem_bytes(k, M == 16 ? kQuadCap : 2048) + 64 + 2 * sizeof(QuadGroup);
 }
 // survivor queue capacity: whatever two CTAs per SM leave (228 KB per SM, 1 KB reserved per CTA), in steps of 256
-__host__ __device__ inline int quad_surv_cap(int d, int k) {
-    const long long room = (228 * 1024 / 2 - 1024 - 256) - static_cast<long long>(quad_smem_fixed(d, k));
+__host__ __device__ inline int quad_surv_cap(int M, int d, int k) {
+    const long long room = (228 * 1024 / 2 - 1024 - 256) - static_cast<long long>(quad_smem_fixed(M, d, k));
     long long cap = room > 0 ? (room / 4) & ~255ll : 0;
     if (cap > kQuadSurvMax) cap = kQuadSurvMax;
     if (cap < kQuadSurvMin) cap = kQuadSurvMin;
     return static_cast<int>(cap);
 }
-__host__ __device__ inline size_t quad_smem_bytes(int d, int k) {
-    return quad_smem_fixed(d, k) + sizeof(uint32_t) * quad_surv_cap(d, k);
+__host__ __device__ inline size_t quad_smem_bytes(int M, int d, int k) {
+    return quad_smem_fixed(M, d, k) + sizeof(uint32_t) * quad_surv_cap(M, d, k);
 }
 
 struct QuadCtrl {          // 64 bytes
@@ -110,6 +124,22 @@ __device__ __forceinline__ uint2 quad_lookup(const char* __restrict__ lutb, uint
     return *reinterpret_cast<const uint2*>(lutb + a + 8 * p);
 }
 
+template <int M>
+struct QuadCode {
+    uint4 v[M / 16];
+};
+template <int M>
+__device__ __forceinline__ QuadCode<M> quad_load_code(const uint4* __restrict__ lp, uint32_t idx, uint32_t n) {
+    QuadCode<M> c;
+#pragma unroll
+    for (int h = 0; h < M / 16; h++) c.v[h] = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < n) {
+#pragma unroll
+        for (int h = 0; h < M / 16; h++) c.v[h] = __ldg(lp + static_cast<size_t>(idx) * (M / 16) + h);
+    }
+    return c;
+}
+
 // the lane's code walked in rotated byte order; returns the four packed lower bounds
 __device__ __forceinline__ uint2 quad_block16(const char* __restrict__ lutb, const uint4& code, bool ws2, bool ws1,
                                               uint32_t bs, uint32_t loff) {
@@ -135,32 +165,35 @@ __device__ __forceinline__ uint2 quad_block16(const char* __restrict__ lutb, con
 }
 
 // DSUB = d / 16 when it is one of the specialised values (residuals held in registers), 0 = generic.
-template <int DSUB>
-__global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanParams p, const float* __restrict__ pq_t) {
-    constexpr int M = 16;
+template <int M, int DSUB>
+__global__ void __launch_bounds__(QuadCfg<M>::kT, QuadCfg<M>::kCtasPerSm)
+scan_quad_kernel(const ScanParams p, const float* __restrict__ pq_t) {
+    using Cfg = QuadCfg<M>;
+    constexpr int kT = Cfg::kT;
+    constexpr int kCap = Cfg::kCap;
     extern __shared__ __align__(1024) unsigned char smem_quad[];
-    uint2* lut16 = reinterpret_cast<uint2*>(smem_quad);
+    uint2* lut16 = reinterpret_cast<uint2*>(smem_quad);                           // kTables tables, 64 KB each
     const char* lutb = reinterpret_cast<const char*>(lut16);
     const int dpad = (p.d + 3) & ~3;
-    float4* res4 = reinterpret_cast<float4*>(smem_quad + kQuadLutBytes);          // [d] (r_0, r_1, r_2, r_3)
+    float4* res4 = reinterpret_cast<float4*>(smem_quad + Cfg::kTables * kQuadLutBytes);   // [d] (r_0, r_1, r_2, r_3)
     unsigned char* tk_base = reinterpret_cast<unsigned char*>(res4 + dpad);
     TopK tk[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) tk[q].bind(tk_base + q * TopK::smem_bytes(p.k, kQuadCap), p.k, kQuadCap);
-    uint32_t* surv = reinterpret_cast<uint32_t*>(tk_base + 4 * TopK::smem_bytes(p.k, kQuadCap));
-    const int surv_cap = quad_surv_cap(p.d, p.k);
+    for (int q = 0; q < 4; q++) tk[q].bind(tk_base + q * TopK::smem_bytes(p.k, kCap), p.k, kCap);
+    uint32_t* surv = reinterpret_cast<uint32_t*>(tk_base + 4 * TopK::smem_bytes(p.k, kCap));
+    const int surv_cap = quad_surv_cap(M, p.d, p.k);
     QuadCtrl* ctrl = reinterpret_cast<QuadCtrl*>(surv + surv_cap);
     QuadGroup* s_grp = reinterpret_cast<QuadGroup*>(ctrl + 1);
-    float4* lutf = p.lutf_scratch + static_cast<size_t>(blockIdx.x) * kQuadScratchFloat4;   // exact LUT [m][c]
+    float4* lutf = p.lutf_scratch + static_cast<size_t>(blockIdx.x) * Cfg::kScratchFloat4;   // exact LUT [m][c]
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int r = lane & (M - 1);
+    const int r = lane & 15;
     const uint32_t loff = static_cast<uint32_t>(r) * 8u;
     const bool ws2 = (r & 8) != 0, ws1 = (r & 4) != 0;
     const uint32_t bs = static_cast<uint32_t>(r & 3) * 8u;
     const int ngroups = p.stats->ngroups;
     const int dsub = DSUB ? DSUB : p.dsub;
-    const int lm = tid & (M - 1), lc0 = tid >> 4;
+    const int lm = tid & (M - 1), lc0 = tid / M;   // LUT build: sub-quantizer lm, code values lc0 + 16 i
 
     int next_work = 0, buf = 0;
     if (tid == 0) {
@@ -191,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
         const int list = grp.list;
         const uint32_t n = grp.n;
         const uint4* lp = reinterpret_cast<const uint4*>(p.codes + grp.beg * M);
+        constexpr float kQ = static_cast<float>(Cfg::kQMax);
 
         uint32_t ext[4];
 #pragma unroll
@@ -232,18 +266,18 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
             b2 = b2 * b2 * 1.0001f;
             b3 = b3 * b3 * 1.0001f;
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
+            for (int o = M / 2; o > 0; o >>= 1) {
                 b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, o));
                 b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, o));
                 b2 = fmaxf(b2, __shfl_xor_sync(0xffffffffu, b2, o));
                 b3 = fmaxf(b3, __shfl_xor_sync(0xffffffffu, b3, o));
             }
-            s0 = b0 > 0.0f ? (2047.0f / b0) * 0.999999f : 0.0f;
-            s1 = b1 > 0.0f ? (2047.0f / b1) * 0.999999f : 0.0f;
-            s2 = b2 > 0.0f ? (2047.0f / b2) * 0.999999f : 0.0f;
-            s3 = b3 > 0.0f ? (2047.0f / b3) * 0.999999f : 0.0f;
+            s0 = b0 > 0.0f ? (kQ / b0) * 0.999999f : 0.0f;
+            s1 = b1 > 0.0f ? (kQ / b1) * 0.999999f : 0.0f;
+            s2 = b2 > 0.0f ? (kQ / b2) * 0.999999f : 0.0f;
+            s3 = b3 > 0.0f ? (kQ / b3) * 0.999999f : 0.0f;
         } else {
-            for (int j = tid; j < p.d; j += kThreads) {
+            for (int j = tid; j < p.d; j += kT) {
                 const float cj = p.cent[static_cast<int64_t>(list) * p.d + j];
                 float4 rr;
                 rr.x = __fsub_rn(p.xq[static_cast<int64_t>(qi[0]) * p.d + j], cj);
@@ -253,8 +287,8 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
                 res4[j] = rr;
             }
             __syncthreads();
-            if (tid < 64) {
-                const int q = tid >> 4, m = tid & 15;
+            if (tid < 4 * M) {
+                const int q = tid / M, m = tid % M;
                 float a = 0.0f;
                 for (int j = 0; j < dsub; j++) {
                     const float4 rr = res4[m * dsub + j];
@@ -263,8 +297,8 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
                 }
                 float b = sqrtf(a) * 1.00001f + p.pq_maxnorm[m];
                 b = b * b * 1.0001f;
-                for (int o = 8; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-                if (m == 0) ctrl->scale[q] = b > 0.0f ? (2047.0f / b) * 0.999999f : 0.0f;
+                for (int o = M / 2; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+                if (m == 0) ctrl->scale[q] = b > 0.0f ? (kQ / b) * 0.999999f : 0.0f;
             }
             __syncthreads();
             s0 = ctrl->scale[0];
@@ -276,12 +310,13 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
 #define QUAD_LUT_STORE(C, T0, T1, T2, T3)                                                          \
     {                                                                                              \
         lutf[lm * 256 + (C)] = make_float4(T0, T1, T2, T3);                                        \
-        const uint32_t u0 = min(static_cast<uint32_t>(__float2uint_rz((T0) * s0)), 2047u),         \
-                       u1 = min(static_cast<uint32_t>(__float2uint_rz((T1) * s1)), 2047u),         \
-                       u2 = min(static_cast<uint32_t>(__float2uint_rz((T2) * s2)), 2047u),         \
-                       u3 = min(static_cast<uint32_t>(__float2uint_rz((T3) * s3)), 2047u);         \
+        const uint32_t u0 = min(static_cast<uint32_t>(__float2uint_rz((T0) * s0)), Cfg::kQMax),    \
+                       u1 = min(static_cast<uint32_t>(__float2uint_rz((T1) * s1)), Cfg::kQMax),    \
+                       u2 = min(static_cast<uint32_t>(__float2uint_rz((T2) * s2)), Cfg::kQMax),    \
+                       u3 = min(static_cast<uint32_t>(__float2uint_rz((T3) * s3)), Cfg::kQMax);    \
         const uint2 e_ = make_uint2(u0 | (u1 << 16), u2 | (u3 << 16));                             \
-        uint2* row_ = lut16 + (C) * 32 + lm;                                                       \
+        /* table lm / 16, row = code value, periodic entries (lm % 16) and (lm % 16) + 16 */       \
+        uint2* row_ = lut16 + (lm >> 4) * (kQuadLutBytes / 8) + (C) * 32 + (lm & 15);              \
         row_[0] = e_;                                                                              \
         row_[16] = e_;                                                                             \
     }
@@ -359,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
         // thresholds.  Called by all threads (CTA-uniform), right after a barrier.
         auto drain = [&]() {
             const int ns = ctrl->nsurv[sphase];
-            for (int base = 0; base < ns; base += kThreads) {
+            for (int base = 0; base < ns; base += kT) {
                 const int s = base + tid;
                 uint32_t idx = 0u, bits = 0u;
                 float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -367,16 +402,20 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
                     const uint32_t e = surv[s];
                     idx = e >> 4;
                     bits = e & 15u;
-                    const uint4 cv = __ldg(lp + idx);
-                    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+                    const QuadCode<M> cc = quad_load_code<M>(lp, idx, n);
 #pragma unroll
-                    for (int m = 0; m < M; m++) {
-                        const uint32_t c = (cw[m >> 2] >> (8 * (m & 3))) & 255u;
-                        const float4 t = lutf[m * 256 + c];     // plain (coherent) load: written by this CTA
-                        a0 = __fadd_rn(a0, t.x);
-                        a1 = __fadd_rn(a1, t.y);
-                        a2 = __fadd_rn(a2, t.z);
-                        a3 = __fadd_rn(a3, t.w);
+                    for (int h = 0; h < M / 16; h++) {
+                        const uint32_t cw[4] = {cc.v[h].x, cc.v[h].y, cc.v[h].z, cc.v[h].w};
+#pragma unroll
+                        for (int mm = 0; mm < 16; mm++) {
+                            const int m = 16 * h + mm;
+                            const uint32_t c = (cw[mm >> 2] >> (8 * (mm & 3))) & 255u;
+                            const float4 t = lutf[m * 256 + c];     // plain (coherent) load: written by this CTA
+                            a0 = __fadd_rn(a0, t.x);
+                            a1 = __fadd_rn(a1, t.y);
+                            a2 = __fadd_rn(a2, t.z);
+                            a3 = __fadd_rn(a3, t.w);
+                        }
                     }
                 }
                 const uint32_t b0 = __float_as_uint(a0), b1 = __float_as_uint(a1), b2 = __float_as_uint(a2),
@@ -385,21 +424,21 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
                 tk[1].push((bits & 2u) && b1 <= th1, make_key(b1, idx));
                 tk[2].push((bits & 4u) && b2 <= th2, make_key(b2, idx));
                 tk[3].push((bits & 8u) && b3 <= th3, make_key(b3, idx));
-                // at most 256 new entries per queue and round: fold when another round could overflow
-                const bool over = tk[0].pending() > kQuadCap - kThreads || tk[1].pending() > kQuadCap - kThreads ||
-                                  tk[2].pending() > kQuadCap - kThreads || tk[3].pending() > kQuadCap - kThreads;
-                if (__syncthreads_or(over) && base + kThreads < ns) {
+                // at most kT new entries per queue and round: fold when another round could overflow
+                const bool over = tk[0].pending() > kCap - kT || tk[1].pending() > kCap - kT ||
+                                  tk[2].pending() > kCap - kT || tk[3].pending() > kCap - kT;
+                if (__syncthreads_or(over) && base + kT < ns) {
 #pragma unroll
-                    for (int q = 0; q < 4; q++) tk[q].flush<kThreads>(ext[q]);
+                    for (int q = 0; q < 4; q++) tk[q].template flush<kT>(ext[q]);
                 }
             }
             // every thread has read its survivors: this counter is next used after the NEXT drain, i.e. several
             // barriers from now, so it can be zeroed without one of its own
             if (tid == 0) ctrl->nsurv[sphase] = 0;
             sphase ^= 1;
-            if (!topk_fold_small<kThreads, 4>(tk, ext)) {
+            if (!topk_fold_small<kT, 4>(tk, ext)) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) tk[q].flush<kThreads>(ext[q]);
+                for (int q = 0; q < 4; q++) tk[q].template flush<kT>(ext[q]);
             }
             th0 = tk[0].threshold();
             th1 = tk[1].threshold();
@@ -408,16 +447,21 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
             refresh_int_thresholds();
         };
 
-        // a4: the filter.  Block b = codes b*256 + tid; every lane walks its own code (no carry between blocks).
-        const uint32_t nblk = (n + 255u) >> 8;
+        // a4: the filter.  Block b = codes b*kT + tid; every lane walks its own code (no carry between blocks).
+        const uint32_t nblk = (n + kT - 1) / kT;
         const uint32_t vm01 = ((vmask & 1u) ? 0x8000u : 0u) | ((vmask & 2u) ? 0x80000000u : 0u);
         const uint32_t vm23 = ((vmask & 4u) ? 0x8000u : 0u) | ((vmask & 8u) ? 0x80000000u : 0u);
-        uint4 c0 = skew_load_code16(lp, tid, n), c1 = skew_load_code16(lp, 256u + tid, n), c2, c3;
+        QuadCode<M> c0 = quad_load_code<M>(lp, tid, n), c1 = quad_load_code<M>(lp, kT + tid, n), c2, c3;
 #define QUAD_ITER(CUR, LOADTO, TB)                                                                   \
     {                                                                                                \
-        LOADTO = skew_load_code16(lp, base + (TB + 2) * 256u, n);                                    \
-        const uint2 lb = quad_block16(lutb, CUR, ws2, ws1, bs, loff);                                \
-        const uint32_t idx = base + TB * 256u;                                                       \
+        LOADTO = quad_load_code<M>(lp, base + (TB + 2) * kT, n);                                     \
+        uint2 lb = quad_block16(lutb, CUR.v[0], ws2, ws1, bs, loff);                                 \
+        if constexpr (M == 32) {                                                                     \
+            const uint2 hi = quad_block16(lutb + kQuadLutBytes, CUR.v[M / 16 - 1], ws2, ws1, bs, loff); \
+            lb.x += hi.x;                                                                            \
+            lb.y += hi.y;                                                                            \
+        }                                                                                            \
+        const uint32_t idx = base + TB * kT;                                                         \
         /* per half: 0x8000 + t - s keeps bit 15 iff s <= t (s, t < 2^15) */                         \
         const uint32_t m01 = (t01 - lb.x) & vm01, m23 = (t23 - lb.y) & vm23;                         \
         const bool hit = idx < n && (m01 | m23) != 0u;                                               \
@@ -432,19 +476,25 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
                              ((m23 >> 28) & 8u);                                                     \
         }                                                                                            \
     }
-        for (uint32_t t0 = 0; t0 < nblk; t0 += kQuadTB) {
-            const uint32_t base = t0 * 256u + tid;
+        // drain once enough survivors are waiting (tight thresholds early are worth more than fewer drains); checked
+        // every 1024 codes (kTileBlocks blocks), except after the last block, which goes straight to the final drain
+#define QUAD_CHECK(NEXT)                                                                             \
+    if ((NEXT) % Cfg::kTileBlocks == 0 && t0 + (NEXT) < nblk) {                                      \
+        const int seen = *reinterpret_cast<volatile int*>(&ctrl->nsurv[sphase]);                     \
+        if (__syncthreads_or(seen > p.quad_drain_at)) drain();                                       \
+    }
+        for (uint32_t t0 = 0; t0 < nblk; t0 += 4) {
+            const uint32_t base = t0 * kT + tid;
             QUAD_ITER(c0, c2, 0)
+            QUAD_CHECK(1)
             if (t0 + 1 < nblk) QUAD_ITER(c1, c3, 1)
+            QUAD_CHECK(2)
             if (t0 + 2 < nblk) QUAD_ITER(c2, c0, 2)
+            QUAD_CHECK(3)
             if (t0 + 3 < nblk) QUAD_ITER(c3, c1, 3)
-            // drain once enough survivors are waiting (tight thresholds early are worth more than fewer drains);
-            // the last tile goes straight to the final drain
-            if (t0 + kQuadTB < nblk) {
-                const int seen = *reinterpret_cast<volatile int*>(&ctrl->nsurv[sphase]);
-                if (__syncthreads_or(seen > p.quad_drain_at)) drain();
-            }
+            QUAD_CHECK(4)
         }
+#undef QUAD_CHECK
 #undef QUAD_ITER
         __syncthreads();
         drain();
@@ -453,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
             if (vmask & (1u << q)) {
                 const int nb = tk[q].count();
                 const uint64_t* s = tk[q].sorted();
-                for (int i = tid; i < nb; i += kThreads) p.out_keys[static_cast<int64_t>(pair[q]) * p.k + i] = s[i];
+                for (int i = tid; i < nb; i += kT) p.out_keys[static_cast<int64_t>(pair[q]) * p.k + i] = s[i];
                 if (tid == 0) {
                     p.out_cnt[pair[q]] = nb;
                     if (nb == p.k) atomicMin(p.qthr + qi[q], static_cast<uint32_t>(s[p.k - 1] >> 32));
@@ -464,26 +514,26 @@ __global__ void __launch_bounds__(kThreads, 2) scan_quad16_kernel(const ScanPara
     }
 }
 
-template <int DSUB>
+template <int M, int DSUB>
 int launch_scan_quad_t(const ScanParams& sp, const float* pq_t, int64_t grid, cudaStream_t st) {
-    size_t smem = quad_smem_bytes(sp.d, sp.k);
-    auto kernel = scan_quad16_kernel<DSUB>;
+    size_t smem = quad_smem_bytes(M, sp.d, sp.k);
+    auto kernel = scan_quad_kernel<M, DSUB>;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    kernel<<<(unsigned)grid, kThreads, smem, st>>>(sp, pq_t);
+    kernel<<<(unsigned)grid, QuadCfg<M>::kT, smem, st>>>(sp, pq_t);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
 // CTAs the kernel will be launched with (the caller sizes the exact-LUT scratch with it): 0 when it does not fit
-template <int DSUB>
+template <int M, int DSUB>
 int quad_grid_t(int d, int k, int64_t npairs, int num_sms) {
-    size_t smem = quad_smem_bytes(d, k);
-    auto kernel = scan_quad16_kernel<DSUB>;
+    size_t smem = quad_smem_bytes(M, d, k);
+    auto kernel = scan_quad_kernel<M, DSUB>;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QuadCfg<M>::kT, smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         return 0;
     }
@@ -492,23 +542,37 @@ int quad_grid_t(int d, int k, int64_t npairs, int num_sms) {
     return static_cast<int>(grid);
 }
 
-inline int quad_grid(int dsub, int d, int k, int64_t npairs, int num_sms) {
-    if (quad_smem_bytes(d, k) > 227 * 1024) return 0;
+inline int quad_grid(int M, int dsub, int d, int k, int64_t npairs, int num_sms) {
+    if (quad_smem_bytes(M, d, k) > 227 * 1024) return 0;
+    if (M == 32) {
+        switch (dsub) {
+            case 4: return quad_grid_t<32, 4>(d, k, npairs, num_sms);
+            case 8: return quad_grid_t<32, 8>(d, k, npairs, num_sms);
+            default: return quad_grid_t<32, 0>(d, k, npairs, num_sms);
+        }
+    }
     switch (dsub) {
-        case 4: return quad_grid_t<4>(d, k, npairs, num_sms);
-        case 6: return quad_grid_t<6>(d, k, npairs, num_sms);
-        case 8: return quad_grid_t<8>(d, k, npairs, num_sms);
-        default: return quad_grid_t<0>(d, k, npairs, num_sms);
+        case 4: return quad_grid_t<16, 4>(d, k, npairs, num_sms);
+        case 6: return quad_grid_t<16, 6>(d, k, npairs, num_sms);
+        case 8: return quad_grid_t<16, 8>(d, k, npairs, num_sms);
+        default: return quad_grid_t<16, 0>(d, k, npairs, num_sms);
     }
 }
 
 // returns 0, or -1 on a launch error (caller reads cudaGetLastError)
 inline int launch_scan_quad(const ScanParams& sp, const float* pq_t, int64_t grid, cudaStream_t st) {
+    if (sp.M == 32) {
+        switch (sp.dsub) {
+            case 4: return launch_scan_quad_t<32, 4>(sp, pq_t, grid, st);
+            case 8: return launch_scan_quad_t<32, 8>(sp, pq_t, grid, st);
+            default: return launch_scan_quad_t<32, 0>(sp, pq_t, grid, st);
+        }
+    }
     switch (sp.dsub) {
-        case 4: return launch_scan_quad_t<4>(sp, pq_t, grid, st);
-        case 6: return launch_scan_quad_t<6>(sp, pq_t, grid, st);
-        case 8: return launch_scan_quad_t<8>(sp, pq_t, grid, st);
-        default: return launch_scan_quad_t<0>(sp, pq_t, grid, st);
+        case 4: return launch_scan_quad_t<16, 4>(sp, pq_t, grid, st);
+        case 6: return launch_scan_quad_t<16, 6>(sp, pq_t, grid, st);
+        case 8: return launch_scan_quad_t<16, 8>(sp, pq_t, grid, st);
+        default: return launch_scan_quad_t<16, 0>(sp, pq_t, grid, st);
     }
 }
 

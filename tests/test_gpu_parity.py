@@ -120,17 +120,20 @@ def test_two_query_scan_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
         _util.assert_bit_equal(I, Ir, "I (duo)")
 
 
-@pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used", [
-    (128, 24, 60000, 103, 5, 10, None),     # group sizes 1..4, several tiles per list
-    (96, 16, 12000, 64, 16, 100, 13),       # dsub 6, k = 100, empty lists, every query probes every list
-    (64, 8, 3000, 1, 8, 10, None),          # one query: every group is a single
-    (256, 12, 5000, 37, 3, 7, None),        # dsub 16: generic LUT build
-    (128, 4, 9000, 200, 4, 1, None),        # k = 1, 200 queries on every list
+@pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used,M", [
+    (128, 24, 60000, 103, 5, 10, None, 16),     # group sizes 1..4, several tiles per list
+    (96, 16, 12000, 64, 16, 100, 13, 16),       # dsub 6, k = 100, empty lists, every query probes every list
+    (64, 8, 3000, 1, 8, 10, None, 16),          # one query: every group is a single
+    (256, 12, 5000, 37, 3, 7, None, 16),        # dsub 16: generic LUT build
+    (128, 4, 9000, 200, 4, 1, None, 16),        # k = 1, 200 queries on every list
+    (128, 24, 60000, 103, 5, 10, None, 32),     # M = 32 (C5 shape, dsub 4): two tables, 10-bit entries
+    (256, 16, 12000, 64, 16, 100, 13, 32),      # M = 32, dsub 8, k = 100, empty lists
+    (192, 6, 2500, 9, 6, 10, None, 32),         # M = 32, dsub 6: generic LUT build
 ])
-def test_four_query_filter_scan_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
+def test_four_query_filter_scan_kernel(oracle, d, nlist, n, nq, nprobe, k, used, M):
     """scan_quad.cuh: integer lower-bound filter + exact evaluation of the survivors.  Must return exactly the oracle's
     results, ties included (many duplicate codes make sure survivors at the threshold are not lost)."""
-    a = _util.make_index_arrays(oracle, 90 + d, d, nlist, 16, n, used_lists=used)
+    a = _util.make_index_arrays(oracle, 90 + d, d, nlist, M, n, used_lists=used)
     if d == 128 and nlist == 4:
         rng = np.random.default_rng(5)
         a["codes"] = np.ascontiguousarray(a["codes"][rng.integers(0, 500, size=a["codes"].shape[0])])   # heavy ties
