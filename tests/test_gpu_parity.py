@@ -167,6 +167,22 @@ def test_two_query_scan_kernel_m32(oracle, d, nlist, n, nq, nprobe, k, used):
         _util.assert_bit_equal(I, Ir, "I (duo32)")
 
 
+@pytest.mark.parametrize("variant,M", [("auto", 16), ("skew", 16), ("auto", 32), ("generic", 8)])
+def test_large_k(oracle, variant, M):
+    """k = 1000 (Faiss-GPU allows up to 2048): the candidate queues fold through the shared-memory bitonic path, most
+    lists return fewer than k results, and unfilled slots come back as FLT_MAX / -1."""
+    d = 64 if M != 32 else 128
+    a = _util.make_index_arrays(oracle, 33 + M, d, 16, M, 30000)
+    xq = _util.make_queries(19, a, 48)
+    for nprobe in (8, 1):
+        Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, 1000)
+        index = _load(a, None if variant == "auto" else variant)
+        index.nprobe = nprobe
+        D, I = index.search(xq, 1000)
+        _util.assert_bit_equal(D, Dr, f"D (k = 1000, {variant}, nprobe {nprobe})")
+        _util.assert_bit_equal(I, Ir, f"I (k = 1000, {variant}, nprobe {nprobe})")
+
+
 def test_search_preassigned(oracle):
     import b200ivfpq as faiss
     a = _util.make_index_arrays(oracle, 9, 128, 20, 16, 6000)
