@@ -12,6 +12,7 @@ from .factory import GpuParameterSpace, ParameterSpace, index_factory
 from .index import METRIC_L2, IndexFlatL2, IndexIVFPQ, InvertedLists, ProductQuantizer
 from .io import read_index, write_index
 from .retriever import AsyncB200Retriever, IndexScanner, LocalB200Retriever
+from .server import B200Client, B200Server
 from .transforms import IndexPreTransform, OPQMatrix, downcast_VectorTransform
 from .shards import DistributedIndexIVFPQ, merge_shards, shard_index, shard_positions
 
@@ -36,4 +37,4 @@ def downcast_index(index):
 
 __all__ = ["IndexFlatL2", "IndexIVFPQ", "index_factory", "ParameterSpace", "GpuParameterSpace", "search_preassigned",
            "read_index", "write_index", "LocalB200Retriever", "AsyncB200Retriever", "IndexScanner", "DistributedIndexIVFPQ", "shard_index",
-           "merge_shards", "IndexPreTransform", "OPQMatrix", "downcast_VectorTransform", "METRIC_L2", "omp_set_num_threads", "vector_to_array", "downcast_index", "launch_count"]
+           "merge_shards", "B200Server", "B200Client", "IndexPreTransform", "OPQMatrix", "downcast_VectorTransform", "METRIC_L2", "omp_set_num_threads", "vector_to_array", "downcast_index", "launch_count"]
