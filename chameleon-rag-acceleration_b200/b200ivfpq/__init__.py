@@ -8,6 +8,9 @@
 Hot path = hand-written sm_100a CUDA kernels behind a C-ABI (include/b200_ivfpq.h); no CPU fallback.
 """
 from ._lib import LIB_PATH, launch_count, load as load_library
+from .compat import (GpuClonerOptions, GpuMultipleClonerOptions, GpuResourcesVector, IntVector, StandardGpuResources,
+                     cvar, deserialize_index, index_cpu_to_all_gpus, index_cpu_to_gpu, index_cpu_to_gpu_multiple,
+                     index_cpu_to_gpus_list, index_gpu_to_cpu, rev_swig_ptr, serialize_index, swig_ptr)
 from .factory import GpuParameterSpace, ParameterSpace, index_factory
 from .index import METRIC_L2, IndexFlatL2, IndexIVFPQ, InvertedLists, ProductQuantizer
 from .io import read_index, write_index
@@ -37,4 +40,7 @@ def downcast_index(index):
 
 __all__ = ["IndexFlatL2", "IndexIVFPQ", "index_factory", "ParameterSpace", "GpuParameterSpace", "search_preassigned",
            "read_index", "write_index", "LocalB200Retriever", "AsyncB200Retriever", "IndexScanner", "DistributedIndexIVFPQ", "shard_index",
-           "merge_shards", "B200Server", "B200Client", "IndexPreTransform", "OPQMatrix", "downcast_VectorTransform", "METRIC_L2", "omp_set_num_threads", "vector_to_array", "downcast_index", "launch_count"]
+           "merge_shards", "B200Server", "B200Client", "IndexPreTransform", "OPQMatrix", "downcast_VectorTransform", "METRIC_L2", "omp_set_num_threads", "vector_to_array", "downcast_index", "launch_count",
+           "StandardGpuResources", "GpuResourcesVector", "IntVector", "GpuClonerOptions", "GpuMultipleClonerOptions",
+           "index_cpu_to_gpu", "index_cpu_to_gpu_multiple", "index_cpu_to_gpus_list", "index_cpu_to_all_gpus",
+           "index_gpu_to_cpu", "serialize_index", "deserialize_index", "swig_ptr", "rev_swig_ptr", "cvar"]

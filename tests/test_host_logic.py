@@ -203,3 +203,24 @@ def test_sass_is_blackwell_native_and_exact():
     for kern in ("coarse_dist_kernel", "encode_kernel", "coarse_exact_flagged_kernel"):
         _, text = ops(kern)
         assert not re.search(r"\bFFMA\b", text), f"contracted FFMA in {kern}"
+
+
+def test_faiss_named_shims():
+    """Names the reference's drivers call around the hot path."""
+    import b200ivfpq as faiss
+    res = faiss.StandardGpuResources()
+    res.setTempMemory(1 << 20)
+    vres, vdev = faiss.GpuResourcesVector(), faiss.IntVector()              # bench_gpu_performance_OSDI.py:492-503
+    vres.push_back(res)
+    vdev.push_back(0)
+    assert vres.size() == 1 and vdev.at(0) == 0
+    co = faiss.GpuMultipleClonerOptions()
+    co.shard, co.useFloat16, co.usePrecomputed, co.indicesOptions = True, False, True, 0      # :587-595
+    idx = faiss.index_factory(64, "IVF16,PQ8")
+    # single process: the index is already on the GPU, cloning is the identity (no process group -> no sharding)
+    assert faiss.index_cpu_to_gpu_multiple(vres, vdev, idx, co) is idx
+    assert faiss.index_cpu_to_gpus_list(idx, co=co, gpus=[0]) is idx and faiss.index_gpu_to_cpu(idx) is idx
+    a = np.arange(10, dtype=np.int64)
+    assert np.array_equal(faiss.rev_swig_ptr(faiss.swig_ptr(a), 4), a[:4])
+    faiss.cvar.indexIVF_stats.reset()
+    assert faiss.cvar.indexIVF_stats.nq == 0 and faiss.cvar.indexIVFPQ_stats.search_cycles == 0
