@@ -241,11 +241,12 @@ def build_index(cfg, rank, world, device, dist, args):
     t0 = time.perf_counter()
     chunk = 1 << 21
     nchunks = (nb + chunk - 1) // chunk
-    for ci in range(rank, nchunks, world):
+    by_list = args.shard_mode in ("list", "replica") and world > 1      # every rank encodes the whole database
+    for ci in (range(nchunks) if by_list else range(rank, nchunks, world)):
         n = min(chunk, nb - ci * chunk)
         x = gen.chunk(SEED_BASE, ci, n)
         pos0 = ci * chunk
-        if ngt:
+        if ngt and ci % world == rank:
             # exact brute force for recall: ||x||^2 - 2 q.x (+ ||q||^2), fp32 library GEMM (not on the timed path)
             dd = torch.addmm((x * x).sum(1).unsqueeze(0), xq_gt, x.t(), alpha=-2.0) + qn
             cd, cidx = torch.topk(dd, 10, dim=1, largest=False)
@@ -269,6 +270,10 @@ def build_index(cfg, rank, world, device, dist, args):
         all_i = all_i.view(world, ngt, 10).permute(1, 0, 2).reshape(ngt, world * 10)
         gt_d, sel = torch.topk(all_d, 10, dim=1, largest=False)
         gt_i = torch.gather(all_i, 1, sel)
+    if by_list and args.shard_mode == "list":
+        # every rank encoded everything; keep the lists this rank owns (l % world == rank)
+        index = faiss.shard_index_by_list(index, rank, world)
+        index.nprobe = nprobe
     index._sync_lists()
     torch.cuda.synchronize()
     t_add = time.perf_counter() - t0
@@ -306,7 +311,7 @@ def run_ours(args):
     if rank == 0:
         log(f"[bench] {workload_name(cfg, args)} on {world} GPU(s)")
     index, xq, gt, build_info = build_index(cfg, rank, world, device, dist, args)
-    searcher = DistributedIndexIVFPQ(index) if world > 1 else index
+    searcher = DistributedIndexIVFPQ(index, shard_mode=args.shard_mode) if world > 1 else index
     index.set_stage_timing(True)
 
     def barrier():
@@ -367,6 +372,14 @@ def run_ours(args):
             stage_acc.setdefault(kk, []).append(v)
     stages = {kk: float(np.mean(v)) for kk, v in stage_acc.items()}
     scan_t = float(np.mean(scan_ms))
+    # every rank's own scan time and scanned bytes (rank 0's line reports them: shard balance)
+    per_rank = torch.tensor([scan_t, float(stats["bytes"]), ms_total / args.steps], dtype=torch.float64, device=device)
+    if world > 1:
+        allr = torch.empty((world, 3), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allr, per_rank)
+    else:
+        allr = per_rank.view(1, 3)
+    allr = allr.cpu().numpy()
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ------------------
     xq_host = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
@@ -460,8 +473,14 @@ def run_ours(args):
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32/u8", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, args), "sharding": f"by vector: 2M-vector chunks round-robin over {world} GPU(s)",
+            "config": {"workload": workload_name(cfg, args), "sharding": (f"by list (NOT the reference's split): list l on GPU l % {world}, probes of other GPUs' lists masked"
+                                    if args.shard_mode == "list" and world > 1 else
+                                    f"replicated (Faiss IndexReplicas, NOT the sharded config): full index on each of "
+                                    f"{world} GPUs, batch sliced by query, results all-gathered"
+                                    if args.shard_mode == "replica" and world > 1 else
+                                    f"by vector: 2M-vector chunks round-robin over {world} GPU(s)"),
                        "shard_merge": ("none" if world == 1 else
+                                       "none: NCCL all-gather of the per-slice results" if args.shard_mode == "replica" else
                                        "K5 reads every shard's top-k in place over NVLink (symmetric memory)"
                                        if getattr(searcher, "peer_merge", False) else
                                        "NCCL all-gather + K5" + (f" (peer memory unavailable: {searcher.peer_merge_error})"
@@ -474,6 +493,9 @@ def run_ours(args):
             "e2e": {"value": e2e_qps, "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * d * 4,
                     "d2h_bytes_per_step": nq * k * 12},
             "latency_batch1_ms_p50": lat_p50, "recall_at_10": recall, "stages_ms": stages,
+            "scan_ms_per_rank": [round(float(v), 3) for v in allr[:, 0]],
+            "scan_gbytes_per_rank": [round(float(v) / 1e9, 2) for v in allr[:, 1]],
+            "ms_per_step_per_rank": [round(float(v), 3) for v in allr[:, 2]],
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_oracle": parity,
         }
         emit(line)
@@ -482,7 +504,7 @@ def run_ours(args):
     return 0
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -500,7 +522,15 @@ def main():
     ap.add_argument("--kmeans-iters", type=int, default=25, help="Lloyd iterations for index.train (Faiss default 25)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+    ap.add_argument("--shard-mode", default="vector", choices=["vector", "list", "replica"],
+                    help="N > 1: 'vector' = the reference's / north_star's split (every list on every GPU); 'list' = "
+                         "whole lists per GPU (l %% world); 'replica' = Faiss IndexReplicas (co.shard = False): full index "
+                         "on every GPU, the batch sliced by query")
+    return ap.parse_args(argv)
+
+
+def main():
+    args = parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: timing rules ask for >= 3 warm-up steps")
     if args.impl == "reference":

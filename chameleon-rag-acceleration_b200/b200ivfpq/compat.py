@@ -78,13 +78,15 @@ class GpuMultipleClonerOptions(GpuClonerOptions):
 
 def _maybe_shard(index, co):
     """Single process: the index is already on the GPU.  torchrun job + co.shard: this rank's modulo shard behind the
-    all-gather / peer-memory merge."""
+    all-gather / peer-memory merge; torchrun job without co.shard: a replica that answers its slice of every batch."""
     import torch.distributed as dist
     from .shards import DistributedIndexIVFPQ, shard_index
-    if co is not None and getattr(co, "shard", False) and dist.is_available() and dist.is_initialized() \
-            and dist.get_world_size() > 1:
+    if co is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         inner = getattr(index, "index", index)
-        return DistributedIndexIVFPQ(shard_index(inner, dist.get_rank(), dist.get_world_size()))
+        if getattr(co, "shard", False):
+            return DistributedIndexIVFPQ(shard_index(inner, dist.get_rank(), dist.get_world_size()))
+        # co.shard = False is Faiss's IndexReplicas: full copy per GPU, queries split between them
+        return DistributedIndexIVFPQ(inner, shard_mode="replica")
     return index
 
 

@@ -1,4 +1,5 @@
-"""Multi-GPU search: inverted lists sharded by vector, per-shard top-k merged after an all-gather.
+"""Multi-GPU search: inverted lists sharded by vector, per-shard top-k merged after an all-gather (the default, and
+what the reference runs); optionally whole lists per GPU, or a replicated index with the batch sliced by query.
 
 Reference behaviour: faiss.index_cpu_to_gpu_multiple(vres, vdev, index, co) with co.shard = True
 (bench_gpu_performance_OSDI.py:586-604), i.e. Faiss IndexShards with the modulo split the reference logs
@@ -53,6 +54,28 @@ def shard_index(index: IndexIVFPQ, rank: int, world: int) -> IndexIVFPQ:
     return sub
 
 
+def shard_index_by_list(index: IndexIVFPQ, rank: int, world: int) -> IndexIVFPQ:
+    """Rank's shard when WHOLE LISTS are distributed: list l lives on rank l % world (all nlist lists exist on every
+    rank, the others are empty).  Not what the reference does (Faiss IndexShards splits by vector), but the layout that
+    removes the per-(query, list) work every by-vector shard repeats: a (query, list) pair is then scanned -- and its
+    LUT built -- on exactly one GPU.  Use with DistributedIndexIVFPQ(..., shard_mode="list")."""
+    index._finalize_lists()
+    sub = IndexIVFPQ(None, index.d, index.nlist, index.pq.M, index.pq.nbits)
+    sub.set_codebooks(index.quantizer.xb_tensor(), index.pq.centroids_tensor())
+    sub.nprobe = index.nprobe
+    off = index._offsets
+    if int(off[-1]) == 0:
+        return sub
+    dev = index._codes.device
+    sizes = np.diff(off)
+    mine = (np.arange(index.nlist) % world) == rank
+    keep_rows = torch.repeat_interleave(torch.from_numpy(mine).to(dev), torch.from_numpy(sizes).to(dev))
+    new_off = np.zeros(index.nlist + 1, np.int64)
+    new_off[1:] = np.cumsum(np.where(mine, sizes, 0))
+    sub.set_lists(new_off, index._codes[keep_rows].contiguous(), index._ids[keep_rows].contiguous())
+    return sub
+
+
 def merge_shards(Ds: torch.Tensor, Is: torch.Tensor):
     """K5 on the current device.  Ds, Is: (nshard, nq, k) CUDA tensors -> (D, I) (nq, k)."""
     lib = _lib.load()
@@ -93,7 +116,8 @@ class DistributedIndexIVFPQ:
     `merge_fn` / `local_search_fn` are injection points for the CPU (gloo) tests of the exchange logic; the
     product path uses the CUDA kernels."""
 
-    def __init__(self, local_index, group=None, merge_fn=None, local_search_fn=None, shard_coarse=True, peer_merge=None):
+    def __init__(self, local_index, group=None, merge_fn=None, local_search_fn=None, shard_coarse=True, peer_merge=None,
+                 shard_mode: str = "vector"):
         import torch.distributed as dist
         self.dist = dist
         self.local = local_index
@@ -104,6 +128,15 @@ class DistributedIndexIVFPQ:
         self._injected_search = local_search_fn
         self.shard_coarse = shard_coarse
         self.d = getattr(local_index, "d", None)
+        if shard_mode not in ("vector", "list", "replica"):
+            raise ValueError("shard_mode must be 'vector', 'list' or 'replica'")
+        # "list": this rank owns the lists l with l % world == rank (shard_index_by_list); probes of other ranks'
+        # lists are masked out before the local scan.
+        # "replica": every rank holds the WHOLE index (Faiss IndexReplicas, GpuMultipleClonerOptions.shard = False);
+        # the batch is sliced by query, each rank answers its slice, one all-gather returns the full result everywhere
+        self.shard_mode = shard_mode
+        if shard_mode == "replica":
+            peer_merge = False
         # Peer-memory merge: every rank's (D, I) lands in a symmetric-memory buffer that all GPUs of the box map into
         # their address space; K5 then reads the shards in place over NVLink / NVSwitch -- no all-gather, no staging
         # copies.  Falls back to the NCCL all-gather when symmetric memory cannot be set up (or B200_IVFPQ_P2P=0).
@@ -137,13 +170,20 @@ class DistributedIndexIVFPQ:
         if self._injected_search is not None:
             return self._injected_search(xq, k)
         nq, nprobe = xq.shape[0], int(self.local.nprobe)
-        if not (self.shard_coarse and self.world > 1 and nq >= 8 * self.world):
+        sliced = self.shard_coarse and self.world > 1 and nq >= 8 * self.world
+        if not sliced and self.shard_mode == "vector":
             return self.local.search(xq, k, out=out) if out is not None else self.local.search(xq, k)
-        # coarse stage on my slice of the queries, then exchange the probe lists
-        bounds = [(nq * r) // self.world for r in range(self.world + 1)]
-        counts = [bounds[r + 1] - bounds[r] for r in range(self.world)]
-        _, ids = self.local.quantizer.search(xq[bounds[self.rank]:bounds[self.rank + 1]], min(nprobe, self.local.nlist))
-        probes = self._all_gather_rows(ids, counts)
+        if sliced:
+            # coarse stage on my slice of the queries, then exchange the probe lists
+            bounds = [(nq * r) // self.world for r in range(self.world + 1)]
+            counts = [bounds[r + 1] - bounds[r] for r in range(self.world)]
+            _, ids = self.local.quantizer.search(xq[bounds[self.rank]:bounds[self.rank + 1]],
+                                                 min(nprobe, self.local.nlist))
+            probes = self._all_gather_rows(ids, counts)
+        else:
+            _, probes = self.local.quantizer.search(xq, min(nprobe, self.local.nlist))
+        if self.shard_mode == "list":
+            probes = torch.where(probes % self.world == self.rank, probes, torch.full_like(probes, -1))
         if out is not None:
             return self.local.search_preassigned(xq, k, probes, out=out)
         return self.local.search_preassigned(xq, k, probes)
@@ -189,7 +229,23 @@ class DistributedIndexIVFPQ:
         self._readers_pending = True
         return D, I
 
+    def _search_replica(self, xq: torch.Tensor, k: int):
+        nq = xq.shape[0]
+        bounds = [(nq * r) // self.world for r in range(self.world + 1)]
+        counts = [bounds[r + 1] - bounds[r] for r in range(self.world)]
+        mine = xq[bounds[self.rank]:bounds[self.rank + 1]]
+        if mine.shape[0]:
+            D, I = self._injected_search(mine, k) if self._injected_search is not None else self.local.search(mine, k)
+        else:   # fewer queries than ranks (the batch-1 latency path): nothing to do here but join the exchange
+            D = torch.empty((0, k), dtype=torch.float32, device=xq.device)
+            I = torch.empty((0, k), dtype=torch.int64, device=xq.device)
+        if self.world == 1:
+            return D, I
+        return unpack_results(self._all_gather_rows(pack_results(D, I), counts))
+
     def search(self, xq: torch.Tensor, k: int):
+        if self.shard_mode == "replica":
+            return self._search_replica(xq, k)
         if self.peer_merge and isinstance(xq, torch.Tensor) and xq.is_cuda:
             try:
                 return self._search_peer(xq, k)

@@ -103,6 +103,7 @@ struct b200_ivfpq_index {
     int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free), 3 = two-query skewed (scan_duo.cuh),
                             // 4 = four-query integer filter + exact survivors (scan_quad.cuh)
     int64_t max_list = 0;   // longest inverted list
+    int64_t nonempty = 0;   // lists holding at least one entry (a by-list shard leaves the others empty)
     int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
     // workspace
     DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t, lutf, pq_maxnorm, lutg;
@@ -411,7 +412,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         int quad_ctas = 0;
         if (quad_supported(h->M, h->d, k) && aligned16 && nseg == 1 && h->max_list < (int64_t)kQuadMaxList &&
             (h->scan_variant == 4 ||
-             (h->scan_variant == 0 && npairs >= 6 * h->nlist && h->ntotal >= kQuadMinAvgList * h->nlist)))
+             (h->scan_variant == 0 && npairs >= 6 * h->nlist && h->ntotal >= kQuadMinAvgList * std::max<int64_t>(h->nonempty, 1))))
             quad_ctas = quad_grid(h->M, h->dsub, h->d, k, npairs, h->num_sms);
         if (h->scan_variant == 4 && quad_ctas == 0)
             return fail(B200_IVFPQ_EUNSUPPORTED, "four-query scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
@@ -656,10 +657,11 @@ int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, const uint8_t
     if (!h_offsets) return fail(B200_IVFPQ_EINVAL, "null offsets");
     if (ntotal < 0 || h_offsets[0] != 0 || h_offsets[h->nlist] != ntotal)
         return fail(B200_IVFPQ_EINVAL, "offsets must start at 0 and end at ntotal");
-    int64_t max_list = 0;
+    int64_t max_list = 0, nonempty = 0;
     for (int64_t l = 0; l < h->nlist; l++) {
         int64_t sz = h_offsets[l + 1] - h_offsets[l];
         max_list = std::max(max_list, sz);
+        nonempty += sz > 0;
         if (sz < 0) return fail(B200_IVFPQ_EINVAL, "offsets not monotone at list %lld", (long long)l);
         if (sz >= (int64_t(1) << 32)) return fail(B200_IVFPQ_EUNSUPPORTED, "list %lld longer than 2^32", (long long)l);
     }
@@ -672,6 +674,7 @@ int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, const uint8_t
     h->ids = d_ids;
     h->ntotal = ntotal;
     h->max_list = max_list;
+    h->nonempty = nonempty;
     h->has_lists = true;
     h->state_epoch++;
     return 0;

@@ -60,7 +60,17 @@ def _worker(rank, world, port, out_dir):
         index = DistributedIndexIVFPQ(_Local(), merge_fn=merge, local_search_fn=local_search)
         assert index.world == world and index.rank == rank
         D, I = index.search(torch.from_numpy(xq), k)
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), D=D.numpy(), I=I.numpy())
+        # replicated index, batch sliced by query (co.shard = False): unequal slices (23 queries) and a batch smaller
+        # than the world (1 query: rank 1 only joins the exchange)
+        def full_search(x, kk):
+            D_, I_ = oracle.C.search(x.numpy(), a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, kk)
+            return torch.from_numpy(D_), torch.from_numpy(I_)
+
+        rep = DistributedIndexIVFPQ(_Local(), local_search_fn=full_search, shard_mode="replica")
+        Dr, Ir = rep.search(torch.from_numpy(xq[:23]), k)
+        D1, I1 = rep.search(torch.from_numpy(xq[:1]), k)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), D=D.numpy(), I=I.numpy(), Dr=Dr.numpy(), Ir=Ir.numpy(),
+                 D1=D1.numpy(), I1=I1.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -77,3 +87,8 @@ def test_world2_gloo_exchange_and_merge(oracle, tmp_path):
     _util.assert_bit_equal(outs[0]["D"], outs[1]["D"], "ranks agree on D")
     _util.assert_bit_equal(outs[0]["I"], outs[1]["I"], "ranks agree on I")
     _util.assert_same_modulo_ties(outs[0]["D"], outs[0]["I"], D, I, "sharded vs single index")
+    for r in range(world):
+        _util.assert_bit_equal(outs[r]["Dr"], D[:23], f"replica D on rank {r}")
+        _util.assert_bit_equal(outs[r]["Ir"], I[:23], f"replica I on rank {r}")
+        _util.assert_bit_equal(outs[r]["D1"], D[:1], f"replica batch-1 D on rank {r}")
+        _util.assert_bit_equal(outs[r]["I1"], I[:1], f"replica batch-1 I on rank {r}")

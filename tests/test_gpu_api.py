@@ -166,6 +166,25 @@ def test_merge_shards_kernel_and_sharded_search(oracle):
         _util.assert_bit_equal(Dm, Do, "K5 vs oracle merge D")
         _util.assert_bit_equal(Im, Io, "K5 vs oracle merge I")
         _util.assert_same_modulo_ties(Dm, Im, D, I, f"sharded x{world} vs single")
+    # whole lists per shard (shard_mode="list"): the probes of the other shards' lists are masked out; since every
+    # (query, list) pair is evaluated exactly once, by the same code, the merged DISTANCES are bit-identical
+    xq_t = torch.from_numpy(xq).cuda()
+    _, probes = index.quantizer.search(xq_t, 8)
+    for world in (2, 3):
+        Ds, Is, tot = [], [], 0
+        for r in range(world):
+            sub = faiss.shard_index_by_list(index, r, world)
+            tot += sub.ntotal
+            sizes = np.diff(sub._offsets)
+            assert not sizes[np.arange(32) % world != r].any()
+            masked = torch.where(probes % world == r, probes, torch.full_like(probes, -1))
+            d_, i_ = sub.search_preassigned(xq_t, 10, masked)
+            Ds.append(d_)
+            Is.append(i_)
+        assert tot == 12000
+        Dm, Im = faiss.merge_shards(torch.stack(Ds), torch.stack(Is))
+        _util.assert_bit_equal(Dm.cpu().numpy(), np.asarray(D), f"list-sharded x{world} D")
+        _util.assert_same_modulo_ties(Dm.cpu().numpy(), Im.cpu().numpy(), D, I, f"list-sharded x{world} vs single")
     # pack / unpack used by the all-gather
     from b200ivfpq.shards import pack_results, unpack_results
     d2, i2 = unpack_results(pack_results(Ds[0], Is[0]))

@@ -35,20 +35,25 @@ def main():
         full = faiss.IndexIVFPQ(faiss.IndexFlatL2(d), d, nlist, M, 8)
         full.set_codebooks(a["coarse"], a["pq"])
         full.set_lists(a["offsets"], a["codes"], a["ids"])
-        local_index = faiss.shard_index(full, rank, world)
-        local_index.nprobe = nprobe
-        index = faiss.DistributedIndexIVFPQ(local_index)
-        D, I = index.search(torch.from_numpy(xq).cuda(), k)
-        torch.cuda.synchronize()
-        if rank == 0:
-            Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
-            try:
-                _util.assert_same_modulo_ties(D.cpu().numpy(), I.cpu().numpy(), Dr, Ir, f"world {world}")
-                print(f"[check_multigpu] world={world} d={d} k={k}: merged result == oracle (modulo ties), "
-                      f"shard sizes ~{local_index.ntotal}")
-            except AssertionError as e:
-                ok = False
-                print("[check_multigpu] MISMATCH", e)
+        for mode in ("vector", "list", "replica"):
+            local_index = (faiss.shard_index(full, rank, world) if mode == "vector"
+                           else faiss.shard_index_by_list(full, rank, world) if mode == "list" else full)
+            local_index.nprobe = nprobe
+            index = faiss.DistributedIndexIVFPQ(local_index, shard_mode=mode)
+            D, I = index.search(torch.from_numpy(xq).cuda(), k)
+            torch.cuda.synchronize()
+            if rank == 0:
+                Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+                try:
+                    _util.assert_same_modulo_ties(D.cpu().numpy(), I.cpu().numpy(), Dr, Ir, f"world {world} {mode}")
+                    print(f"[check_multigpu] world={world} d={d} k={k} sharded by {mode}: merged result == oracle "
+                          f"(modulo ties), shard sizes ~{local_index.ntotal}, "
+                          f"merge = {'peer memory' if index.peer_merge else 'NCCL all-gather'}")
+                    if mode == "replica":   # no merge at all: same kernels on the same lists as the single-GPU search
+                        assert np.array_equal(I.cpu().numpy(), Ir), "replica ids differ from the oracle"
+                except AssertionError as e:
+                    ok = False
+                    print("[check_multigpu] MISMATCH", e)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
