@@ -246,7 +246,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def build_index(cfg, rank, world, device, dist, args):
+def build_index(cfg, rank, world, device, dist, args, layout=None):
     """Generate -> train -> assign/encode -> discard, chunk by chunk on the GPU.  Rank r
     keeps the 2M-vector chunks c with c % world == r.  Exact ground truth for a query sample is computed alongside."""
     import torch
@@ -290,12 +290,16 @@ def build_index(cfg, rank, world, device, dist, args):
     t0 = time.perf_counter()
     chunk = 1 << 21
     nchunks = (nb + chunk - 1) // chunk
-    by_list = args.shard_mode in ("list", "replica") and world > 1      # every rank encodes the whole database
-    for ci in (range(nchunks) if by_list else range(rank, nchunks, world)):
+    # With R replicas of S = world / R shards each (--replicas R; `--shard-mode replica` is R = world), a rank holds shard
+    # `sh` of S: the chunks c % S == sh.  layout = (S, sh, shard_group); the ground truth is merged inside the shard group.
+    S, sh, shard_group = layout or (world, rank, None)
+    by_list = args.shard_mode == "list" and world > 1        # every rank encodes everything, then keeps its lists
+    gS, gsh, ggroup = (world, rank, None) if by_list else (S, sh, shard_group)      # who ground-truths which chunk
+    for ci in (range(nchunks) if by_list else range(sh, nchunks, S)):
         n = min(chunk, nb - ci * chunk)
         x = gen.chunk(SEED_BASE, ci, n)
         pos0 = ci * chunk
-        if ngt and ci % world == rank:
+        if ngt and ci % gS == gsh:
             # exact brute force for recall: ||x||^2 - 2 q.x (+ ||q||^2), fp32 library GEMM (not on the timed path)
             dd = torch.addmm((x * x).sum(1).unsqueeze(0), xq_gt, x.t(), alpha=-2.0) + qn
             cd, cidx = torch.topk(dd, 10, dim=1, largest=False)
@@ -306,20 +310,20 @@ def build_index(cfg, rank, world, device, dist, args):
             del dd
         index.add_with_ids(x, torch.arange(pos0, pos0 + n, device=device))
         del x
-        if rank == 0 and ((ci // world) % 10 == 0 or ci + world >= nchunks):
+        if rank == 0 and ((ci // S) % 10 == 0 or ci + S >= nchunks):
             torch.cuda.synchronize()
             log(f"[build] chunk {ci + 1}/{nchunks}  {time.perf_counter() - t0:.1f} s")
-    if world > 1 and ngt:
+    if gS > 1 and ngt:
         # merge the per-rank ground truth
-        all_d = torch.empty((world * ngt, 10), device=device)
-        all_i = torch.empty((world * ngt, 10), dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(all_d, gt_d.contiguous())
-        dist.all_gather_into_tensor(all_i, gt_i.contiguous())
-        all_d = all_d.view(world, ngt, 10).permute(1, 0, 2).reshape(ngt, world * 10)
-        all_i = all_i.view(world, ngt, 10).permute(1, 0, 2).reshape(ngt, world * 10)
+        all_d = torch.empty((gS * ngt, 10), device=device)
+        all_i = torch.empty((gS * ngt, 10), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(all_d, gt_d.contiguous(), group=ggroup)
+        dist.all_gather_into_tensor(all_i, gt_i.contiguous(), group=ggroup)
+        all_d = all_d.view(gS, ngt, 10).permute(1, 0, 2).reshape(ngt, gS * 10)
+        all_i = all_i.view(gS, ngt, 10).permute(1, 0, 2).reshape(ngt, gS * 10)
         gt_d, sel = torch.topk(all_d, 10, dim=1, largest=False)
         gt_i = torch.gather(all_i, 1, sel)
-    if by_list and args.shard_mode == "list":
+    if by_list:
         # every rank encoded everything; keep the lists this rank owns (l % world == rank)
         index = faiss.shard_index_by_list(index, rank, world)
         index.nprobe = nprobe
@@ -359,8 +363,25 @@ def run_ours(args):
     nb, d, nlist, M, nprobe, k, nq = cfg
     if rank == 0:
         log(f"[bench] {workload_name(cfg, args)} on {world} GPU(s)")
-    index, xq, gt, build_info = build_index(cfg, rank, world, device, dist, args)
-    searcher = DistributedIndexIVFPQ(index, shard_mode=args.shard_mode) if world > 1 else index
+    # multi-GPU layout: R replicas x S shards by vector (default R = 1: the reference's co.shard = True over all GPUs)
+    R = world if args.shard_mode == "replica" else max(1, args.replicas)
+    if world % R or (R > 1 and args.shard_mode == "list"):
+        raise SystemExit(f"--replicas {R} must divide the number of GPUs ({world}) and needs --shard-mode vector")
+    layout = None
+    if world > 1 and R == world:
+        layout = (1, 0, None)                                 # every rank holds (and builds) the whole index
+    elif world > 1 and R > 1:
+        from b200ivfpq.shards import IndexReplicas, make_replica_groups, replica_layout
+        S, rep, sh = replica_layout(world, rank, R)
+        shard_group, cross_group = make_replica_groups(R)
+        layout = (S, sh, shard_group)
+    index, xq, gt, build_info = build_index(cfg, rank, world, device, dist, args, layout)
+    if world == 1:
+        searcher = index
+    elif R == 1 or R == world:
+        searcher = DistributedIndexIVFPQ(index, shard_mode="replica" if R == world else args.shard_mode)
+    else:
+        searcher = IndexReplicas(DistributedIndexIVFPQ(index, group=shard_group), R, rep, cross_group)
     index.set_stage_timing(True)
 
     def barrier():
@@ -526,10 +547,12 @@ def run_ours(args):
                                     if args.shard_mode == "list" and world > 1 else
                                     f"replicated (Faiss IndexReplicas, NOT the sharded config): full index on each of "
                                     f"{world} GPUs, batch sliced by query, results all-gathered"
-                                    if args.shard_mode == "replica" and world > 1 else
+                                    if R == world and world > 1 else
+                                    f"{R} replicas (batch sliced by query) x {world // R} shards by vector (the reference's "
+                                    f"-R {R}); NOT the all-GPU sharded config" if R > 1 else
                                     f"by vector: 2M-vector chunks round-robin over {world} GPU(s)"),
                        "shard_merge": ("none" if world == 1 else
-                                       "none: NCCL all-gather of the per-slice results" if args.shard_mode == "replica" else
+                                       "none: NCCL all-gather of the per-slice results" if R == world else
                                        "K5 reads every shard's top-k in place over NVLink (symmetric memory)"
                                        if getattr(searcher, "peer_merge", False) else
                                        "NCCL all-gather + K5" + (f" (peer memory unavailable: {searcher.peer_merge_error})"
@@ -571,6 +594,9 @@ def parse_args(argv=None):
     ap.add_argument("--kmeans-iters", type=int, default=25, help="Lloyd iterations for index.train (Faiss default 25)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", type=int, default=1,
+                    help="N > 1: R replica groups of N/R vector shards each, the batch sliced by query between the "
+                         "groups (the reference's -R, bench_gpu_performance_OSDI.py:613-626); default 1 = all GPUs shard")
     ap.add_argument("--shard-mode", default="vector", choices=["vector", "list", "replica"],
                     help="N > 1: 'vector' = the reference's / north_star's split (every list on every GPU); 'list' = "
                          "whole lists per GPU (l %% world); 'replica' = Faiss IndexReplicas (co.shard = False): full index "

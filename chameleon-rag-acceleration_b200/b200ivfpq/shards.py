@@ -104,6 +104,97 @@ def unpack_results(buf: torch.Tensor):
     return D, I
 
 
+def all_gather_rows(dist, group, world: int, mine: torch.Tensor, counts):
+    """all-gather of row blocks of unequal height (padded to the largest block): rank r of `group` contributes
+    counts[r] rows; everyone gets the blocks stacked in rank order."""
+    hmax = max(counts)
+    pad = mine
+    if mine.shape[0] < hmax:
+        pad = torch.cat([mine, mine.new_zeros((hmax - mine.shape[0],) + mine.shape[1:])], 0)
+    out = torch.empty((world * hmax,) + mine.shape[1:], dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    out = out.view((world, hmax) + mine.shape[1:])
+    return torch.cat([out[r, :counts[r]] for r in range(world)], 0)
+
+
+def replica_layout(world: int, rank: int, replicas: int):
+    """R replica groups of S = world / R consecutive ranks (the reference's `-R`: GPUs [ngpu*i/R, ngpu*(i+1)/R) form
+    replica i, bench_gpu_performance_OSDI.py:613-626).  Returns (S, replica id, shard rank inside the replica)."""
+    if replicas < 1 or world % replicas:
+        raise ValueError(f"replicas = {replicas} must divide the world size {world}")
+    S = world // replicas
+    return S, rank // S, rank % S
+
+
+def make_replica_groups(replicas: int):
+    """Collective (every rank of the default group calls it): the process groups of the R x S layout.  Returns
+    (shard_group, cross_group): my replica's S ranks (probe exchange + top-k merge) and the R ranks holding the same
+    shard in the other replicas (exchange of the per-replica result slices)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    S, rep, sh = replica_layout(world, rank, replicas)
+    shard_group = cross_group = None
+    for r in range(replicas):                       # new_group is collective over the default group: same order everywhere
+        g = dist.new_group(list(range(r * S, (r + 1) * S)))
+        if r == rep:
+            shard_group = g
+    for j in range(S):
+        g = dist.new_group(list(range(j, world, S)))
+        if j == sh:
+            cross_group = g
+    return shard_group, cross_group
+
+
+class _FnIndex:
+    """search(xq, k) from a plain function (the CPU tests' injection point)."""
+
+    def __init__(self, fn):
+        self.search = fn
+
+
+class IndexReplicas:
+    """Faiss IndexReplicas in SPMD form: R replicas of the same index, every batch sliced by query between them.
+
+    `inner` answers this replica's slice -- an IndexIVFPQ holding the whole index (R = world), or a
+    DistributedIndexIVFPQ over this replica's shard group (R replicas x S shards).  `cross_group` holds one rank of
+    every replica (make_replica_groups); the slices are exchanged with one all-gather over it, so every rank returns
+    the full (nq, k) answer like the reference's single host process does."""
+
+    def __init__(self, inner, replicas: int | None = None, replica_id: int | None = None, cross_group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.inner = inner
+        self.group = cross_group
+        live = dist.is_initialized()
+        self.replicas = replicas if replicas is not None else (dist.get_world_size(cross_group) if live else 1)
+        self.replica_id = replica_id if replica_id is not None else (dist.get_rank(cross_group) if live else 0)
+        self.d = getattr(inner, "d", None)
+        self.peer_merge = getattr(inner, "peer_merge", False)
+        self.peer_merge_error = getattr(inner, "peer_merge_error", None)
+
+    @property
+    def nprobe(self):
+        return self.inner.nprobe
+
+    @nprobe.setter
+    def nprobe(self, v):
+        self.inner.nprobe = v
+
+    def search(self, xq: torch.Tensor, k: int):
+        nq, R = xq.shape[0], self.replicas
+        bounds = [(nq * r) // R for r in range(R + 1)]
+        counts = [bounds[r + 1] - bounds[r] for r in range(R)]
+        mine = xq[bounds[self.replica_id]:bounds[self.replica_id + 1]]
+        if mine.shape[0]:
+            D, I = self.inner.search(mine, k)
+        else:   # fewer queries than replicas (the batch-1 latency path): nothing to do here but join the exchange
+            D = torch.empty((0, k), dtype=torch.float32, device=xq.device)
+            I = torch.empty((0, k), dtype=torch.int64, device=xq.device)
+        if R == 1:
+            return D, I
+        return unpack_results(all_gather_rows(self.dist, self.group, R, pack_results(D, I), counts))
+
+
 class DistributedIndexIVFPQ:
     """The rank-local view of a sharded index.
 
@@ -135,8 +226,13 @@ class DistributedIndexIVFPQ:
         # "replica": every rank holds the WHOLE index (Faiss IndexReplicas, GpuMultipleClonerOptions.shard = False);
         # the batch is sliced by query, each rank answers its slice, one all-gather returns the full result everywhere
         self.shard_mode = shard_mode
+        self._replicas = None
         if shard_mode == "replica":
             peer_merge = False
+            inner = local_index if local_search_fn is None else _FnIndex(local_search_fn)
+            self._replicas = IndexReplicas(inner, self.world, self.rank, group)
+        if peer_merge is None and group is not None and dist.is_initialized() and group is not dist.group.WORLD:
+            peer_merge = False      # symmetric memory over a subgroup (R x S layouts) is opt-in: not yet run on hardware
         # Peer-memory merge: every rank's (D, I) lands in a symmetric-memory buffer that all GPUs of the box map into
         # their address space; K5 then reads the shards in place over NVLink / NVSwitch -- no all-gather, no staging
         # copies.  Falls back to the NCCL all-gather when symmetric memory cannot be set up (or B200_IVFPQ_P2P=0).
@@ -156,15 +252,7 @@ class DistributedIndexIVFPQ:
         self.local.nprobe = v
 
     def _all_gather_rows(self, mine: torch.Tensor, counts):
-        """all-gather of row blocks of unequal height (padded to the largest block)."""
-        hmax = max(counts)
-        pad = mine
-        if mine.shape[0] < hmax:
-            pad = torch.cat([mine, mine.new_zeros((hmax - mine.shape[0],) + mine.shape[1:])], 0)
-        out = torch.empty((self.world * hmax,) + mine.shape[1:], dtype=mine.dtype, device=mine.device)
-        self.dist.all_gather_into_tensor(out, pad.contiguous(), group=self.group)
-        out = out.view((self.world, hmax) + mine.shape[1:])
-        return torch.cat([out[r, :counts[r]] for r in range(self.world)], 0)
+        return all_gather_rows(self.dist, self.group, self.world, mine, counts)
 
     def _local_search(self, xq: torch.Tensor, k: int, out=None):
         if self._injected_search is not None:
@@ -229,23 +317,9 @@ class DistributedIndexIVFPQ:
         self._readers_pending = True
         return D, I
 
-    def _search_replica(self, xq: torch.Tensor, k: int):
-        nq = xq.shape[0]
-        bounds = [(nq * r) // self.world for r in range(self.world + 1)]
-        counts = [bounds[r + 1] - bounds[r] for r in range(self.world)]
-        mine = xq[bounds[self.rank]:bounds[self.rank + 1]]
-        if mine.shape[0]:
-            D, I = self._injected_search(mine, k) if self._injected_search is not None else self.local.search(mine, k)
-        else:   # fewer queries than ranks (the batch-1 latency path): nothing to do here but join the exchange
-            D = torch.empty((0, k), dtype=torch.float32, device=xq.device)
-            I = torch.empty((0, k), dtype=torch.int64, device=xq.device)
-        if self.world == 1:
-            return D, I
-        return unpack_results(self._all_gather_rows(pack_results(D, I), counts))
-
     def search(self, xq: torch.Tensor, k: int):
-        if self.shard_mode == "replica":
-            return self._search_replica(xq, k)
+        if self._replicas is not None:
+            return self._replicas.search(xq, k)
         if self.peer_merge and isinstance(xq, torch.Tensor) and xq.is_cuda:
             try:
                 return self._search_peer(xq, k)

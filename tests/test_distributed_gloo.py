@@ -75,6 +75,84 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _worker_rxs(rank, world, port, out_dir):
+    """2 replicas x 2 shards (the reference's `-R 2` on 4 GPUs, bench_gpu_performance_OSDI.py:613-626)."""
+    for p in (ROOT, os.path.join(ROOT, "chameleon-rag-acceleration_b200"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    from oracle import ivfpq_oracle as oracle
+    from b200ivfpq.shards import DistributedIndexIVFPQ, IndexReplicas, make_replica_groups, replica_layout
+    import _util as U
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        R = 2
+        S, rep, sh = replica_layout(world, rank, R)
+        assert (S, rep, sh) == (2, rank // 2, rank % 2)
+        shard_group, cross_group = make_replica_groups(R)
+        a = U.make_index_arrays(oracle, 17, 32, 16, 8, 3000, id_scramble=False)
+        xq = U.make_queries(6, a, 24)
+        nprobe, k = 5, 10
+        sizes = np.diff(a["offsets"])
+        list_no = np.repeat(np.arange(16), sizes)
+        keep = (a["ids"] % S) == sh                           # this replica's shard `sh` of S
+        off = np.zeros(17, np.int64)
+        off[1:] = np.cumsum(np.bincount(list_no[keep], minlength=16))
+        codes, ids = a["codes"][keep], a["ids"][keep]
+        seen = []
+
+        def local_search(x, kk):
+            seen.append(x.shape[0])
+            D, I = oracle.C.search(x.numpy(), a["coarse"], a["pq"], off, codes, ids, nprobe, kk)
+            return torch.from_numpy(D), torch.from_numpy(I)
+
+        def merge(Ds, Is):
+            D, I = oracle.C.merge_shards(Ds.numpy(), Is.numpy())
+            return torch.from_numpy(D), torch.from_numpy(I)
+
+        class _Local:
+            nprobe = 5
+            d = 32
+
+        inner = DistributedIndexIVFPQ(_Local(), group=shard_group, merge_fn=merge, local_search_fn=local_search)
+        assert inner.world == S and inner.rank == sh and not inner.peer_merge
+        index = IndexReplicas(inner, R, rep, cross_group)
+        D, I = index.search(torch.from_numpy(xq[:23]), k)
+        assert seen == [11 if rep == 0 else 12]               # each replica searched only its slice
+        D1, I1 = index.search(torch.from_numpy(xq[:1]), k)    # batch 1: replica 1 (the last slice) answers
+        assert seen == ([11] if rep == 0 else [12, 1])
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), D=D.numpy(), I=I.numpy(), D1=D1.numpy(), I1=I1.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world4_two_replicas_of_two_shards(oracle, tmp_path):
+    world = 4
+    port = _free_port()
+    mp.spawn(_worker_rxs, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a = _util.make_index_arrays(oracle, 17, 32, 16, 8, 3000, id_scramble=False)
+    xq = _util.make_queries(6, a, 24)
+    D, I = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 5, 10)
+    outs = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    for r in range(world):
+        _util.assert_bit_equal(outs[r]["D"], outs[0]["D"], f"rank {r} agrees with rank 0 on D")
+        _util.assert_bit_equal(outs[r]["I"], outs[0]["I"], f"rank {r} agrees with rank 0 on I")
+        _util.assert_same_modulo_ties(outs[r]["D"], outs[r]["I"], D[:23], I[:23], f"2x2 layout vs single index, rank {r}")
+        _util.assert_same_modulo_ties(outs[r]["D1"], outs[r]["I1"], D[:1], I[:1], f"2x2 layout batch 1, rank {r}")
+
+
+def test_replica_layout_rules():
+    sys.path.insert(0, os.path.join(ROOT, "chameleon-rag-acceleration_b200"))
+    from b200ivfpq.shards import replica_layout
+    assert replica_layout(8, 5, 1) == (8, 0, 5)
+    assert replica_layout(8, 5, 2) == (4, 1, 1)
+    assert replica_layout(8, 5, 8) == (1, 5, 0)
+    with pytest.raises(ValueError):
+        replica_layout(8, 0, 3)
+
+
 @pytest.mark.timeout(300)
 def test_world2_gloo_exchange_and_merge(oracle, tmp_path):
     world = 2
