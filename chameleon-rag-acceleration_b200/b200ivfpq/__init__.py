@@ -17,7 +17,8 @@ from .io import read_index, write_index
 from .retriever import AsyncB200Retriever, IndexScanner, LocalB200Retriever
 from .server import B200Client, B200Server
 from .transforms import IndexPreTransform, OPQMatrix, downcast_VectorTransform
-from .shards import DistributedIndexIVFPQ, merge_shards, shard_index, shard_index_by_list, shard_positions
+from .shards import (DistributedIndexIVFPQ, IndexReplicas, make_replica_groups, merge_shards, replica_layout, shard_index,
+                     shard_index_by_list, shard_positions)
 
 
 def search_preassigned(index, xq, k, list_ids, coarse_dis=None):
@@ -39,7 +40,7 @@ def downcast_index(index):
 
 
 __all__ = ["IndexFlatL2", "IndexIVFPQ", "index_factory", "ParameterSpace", "GpuParameterSpace", "search_preassigned",
-           "read_index", "write_index", "LocalB200Retriever", "AsyncB200Retriever", "IndexScanner", "DistributedIndexIVFPQ", "shard_index", "shard_index_by_list",
+           "read_index", "write_index", "LocalB200Retriever", "AsyncB200Retriever", "IndexScanner", "DistributedIndexIVFPQ", "IndexReplicas", "make_replica_groups", "replica_layout", "shard_index", "shard_index_by_list",
            "merge_shards", "B200Server", "B200Client", "IndexPreTransform", "OPQMatrix", "downcast_VectorTransform", "METRIC_L2", "omp_set_num_threads", "vector_to_array", "downcast_index", "launch_count",
            "StandardGpuResources", "GpuResourcesVector", "IntVector", "GpuClonerOptions", "GpuMultipleClonerOptions",
            "index_cpu_to_gpu", "index_cpu_to_gpu_multiple", "index_cpu_to_gpus_list", "index_cpu_to_all_gpus",
