@@ -282,3 +282,52 @@ def recall_at_k(I, gt, k):
 
 def r1_at_k(I, gt, k):
     return float((I[:, :k] == gt[:, :1]).sum()) / I.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Faiss-CPU's own distance form (use_precomputed_table = 1), restated from upstream faiss 1.7.x IndexIVFPQ.cpp
+# (precompute_table / IVFPQScannerT::precompute_list_tables_L2); the source is NOT under /root/reference.
+# It is NOT the parity contract (that is the residual-LUT form above, the notebook's); it exists to measure how far
+# the two forms are apart -- the reason BASELINE states a 1e-5 relative tolerance instead of bit-exactness.
+# ---------------------------------------------------------------------------------------------------------
+def np_precomputed_table(centroids, pq):
+    """P[l][m][c] = ||p_mc||^2 + 2 <c_l[m], p_mc>   (nlist, M, ksub) fp32."""
+    centroids, pq = _f32(centroids), _f32(pq)
+    M, ksub, dsub = pq.shape
+    cm = centroids.reshape(centroids.shape[0], M, dsub)
+    norms = np.einsum("mkj,mkj->mk", pq, pq).astype(np.float32)
+    ip = np.einsum("lmj,mkj->lmk", cm, pq).astype(np.float32)
+    return (norms[None] + np.float32(2.0) * ip).astype(np.float32)
+
+
+def np_search_preassigned_precomputed(xq, centroids, pq, offsets, codes, ids, probe_ids, k, table=None):
+    """dis = ||q - c_l||^2 + sum_m (P[l][m][code_m] - 2 <q_m, p_m,code_m>), fp32, sum over m ascending from dis0."""
+    xq, centroids, pq = _f32(xq), _f32(centroids), _f32(pq)
+    M, ksub, dsub = pq.shape
+    P = np_precomputed_table(centroids, pq) if table is None else table
+    nq = xq.shape[0]
+    D = np.full((nq, k), FLT_MAX, np.float32)
+    I = np.full((nq, k), -1, np.int64)
+    for q in range(nq):
+        qip = np.einsum("mj,mkj->mk", xq[q].reshape(M, dsub), pq).astype(np.float32)      # <q_m, p_mc>
+        dd, ii = [], []
+        for l in probe_ids[q]:
+            if l < 0:
+                continue
+            beg, end = int(offsets[l]), int(offsets[l + 1])
+            if end == beg:
+                continue
+            T = (P[l] - np.float32(2.0) * qip).astype(np.float32)
+            acc = np.full(end - beg, np_l2sqr_rows(xq[q], centroids[l:l + 1])[0], np.float32)
+            cc = codes[beg:end]
+            for m in range(M):
+                acc = (acc + T[m, cc[:, m]]).astype(np.float32)
+            dd.append(acc)
+            ii.append(ids[beg:end])
+        if not dd:
+            continue
+        dd, ii = np.concatenate(dd), np.concatenate(ii)
+        order = np.lexsort((np.arange(dd.shape[0]), dd))[:k]
+        D[q, :order.shape[0]] = dd[order]
+        I[q, :order.shape[0]] = ii[order]
+    return D, I

@@ -165,3 +165,29 @@ def test_recall_formulas(oracle):
     assert oracle.recall_at_k(I, gt, 3) == pytest.approx(3 / 6)
     assert oracle.r1_at_k(I, gt, 3) == pytest.approx(1 / 2)
     assert oracle.r1_at_k(I, gt, 1) == 0.0
+
+
+@pytest.mark.parametrize("scale,sigma", [(1.0, 0.05), (1.0, 0.01), (255.0, 0.02)])
+def test_faiss_precomputed_table_form_stays_inside_the_stated_tolerance(oracle, scale, sigma):
+    """Faiss-CPU evaluates dis0 + sum_m (P[l][m][code] - 2 <q_m, p>) (use_precomputed_table = 1), the
+    contract here is the notebook's residual-LUT form.  The two are not bit-identical; north_star's tolerance (distances
+    within 1e-5 relative, ids equal except ties) has to cover the gap -- measured here on clustered data at SIFT-like
+    (0..255) and unit scales."""
+    rng = np.random.default_rng(0)
+    d, nlist, M, n, nq, nprobe, k = 128, 32, 16, 6000, 24, 8, 10
+    coarse = (rng.random((nlist, d), dtype=np.float32) * scale).astype(np.float32)
+    pq = (rng.standard_normal((M, 256, d // M)).astype(np.float32) * sigma * scale).astype(np.float32)
+    off = np.zeros(nlist + 1, np.int64)
+    off[1:] = np.cumsum(rng.multinomial(n, np.full(nlist, 1 / nlist)))
+    codes = rng.integers(0, 256, (n, M), dtype=np.uint8)
+    ids = np.arange(n, dtype=np.int64)
+    xq = (coarse[rng.integers(0, nlist, nq)] + rng.standard_normal((nq, d)).astype(np.float32) * sigma * scale)
+    xq = xq.astype(np.float32)
+    _, pid = oracle.C.coarse(xq, coarse, nprobe)
+    D, I = oracle.C.search_preassigned(xq, coarse, pq, off, codes, ids, pid, k)
+    D2, I2 = oracle.np_search_preassigned_precomputed(xq, coarse, pq, off, codes, ids, pid, k)
+    rel = np.abs(D - D2) / np.abs(D)
+    assert rel.max() < 1e-5, rel.max()
+    assert rel.max() > 0, "the two forms are expected to differ in the last bits"
+    same_sets = np.mean([len(set(a) & set(b)) / k for a, b in zip(I, I2)])
+    assert same_sets >= 0.99
