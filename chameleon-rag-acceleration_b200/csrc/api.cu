@@ -105,6 +105,7 @@ struct b200_ivfpq_index {
     int64_t max_list = 0;   // longest inverted list
     int64_t nonempty = 0;   // lists holding at least one entry (a by-list shard leaves the others empty)
     int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
+    int quad_drain_at = 256;   // B200_IVFPQ_QUAD_DRAIN: survivors queued per query slot before the exact evaluation runs
     // workspace
     DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t, lutf, pq_maxnorm, lutg;
     DevBuf host_xq, host_D, host_I;
@@ -472,10 +473,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.nseg = nseg;
         sp.lutg = nullptr;
         sp.negzero2 = 0x8000000080000000ull;
-        {
-            const char* v = getenv("B200_IVFPQ_QUAD_DRAIN");
-            sp.quad_drain_at = v ? std::max(0, std::min(256, atoi(v))) : 256;
-        }
+        sp.quad_drain_at = h->quad_drain_at;
         bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
         if (nseg > 1 && npairs <= 1024) {
             // small batches: every pair is scanned by nseg CTAs -- build its LUT once instead of nseg times
@@ -579,14 +577,20 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     h->M = m;
     h->nbits = nbits;
     h->dsub = d / m;
-    CUDA_TRY(cudaGetDevice(&h->device));
-    CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    cudaError_t e2 = cudaGetDevice(&h->device);
+    if (e2 == cudaSuccess) e2 = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (e2 != cudaSuccess) {
+        delete h;
+        return fail(B200_IVFPQ_ECUDA, "cannot query the current CUDA device: %s", cudaGetErrorString(e2));
+    }
     const char* v = getenv("B200_IVFPQ_SCAN");
     if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : !strcmp(v, "duo") ? 3 : !strcmp(v, "quad") ? 4 : 0;
     v = getenv("B200_IVFPQ_GRAPH");
     if (v) h->use_graph = atoi(v) != 0;
     v = getenv("B200_IVFPQ_NSEG");
     if (v) h->force_nseg = std::max(0, std::min(16, atoi(v)));
+    v = getenv("B200_IVFPQ_QUAD_DRAIN");
+    if (v) h->quad_drain_at = std::max(0, std::min(256, atoi(v)));
     v = getenv("B200_IVFPQ_COARSE");
     if (v) h->coarse_variant = !strcmp(v, "exact") ? 1 : !strcmp(v, "matrix") ? 2 : 0;
     *out = h;

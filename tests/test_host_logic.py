@@ -224,3 +224,11 @@ def test_faiss_named_shims():
     assert np.array_equal(faiss.rev_swig_ptr(faiss.swig_ptr(a), 4), a[:4])
     faiss.cvar.indexIVF_stats.reset()
     assert faiss.cvar.indexIVF_stats.nq == 0 and faiss.cvar.indexIVFPQ_stats.search_cycles == 0
+    # `from faiss.contrib.ivf_tools import search_preassigned` (faiss_server.py:24): forwards to the index method
+    from b200ivfpq.contrib.ivf_tools import search_preassigned
+
+    class _Probe:
+        def search_preassigned(self, xq, k, list_nos):
+            return ("called", k, list_nos)
+
+    assert search_preassigned(_Probe(), None, 7, [[1, -1]], coarse_dis=None) == ("called", 7, [[1, -1]])
