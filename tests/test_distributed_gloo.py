@@ -69,6 +69,22 @@ def _worker(rank, world, port, out_dir):
         rep = DistributedIndexIVFPQ(_Local(), local_search_fn=full_search, shard_mode="replica")
         Dr, Ir = rep.search(torch.from_numpy(xq[:23]), k)
         D1, I1 = rep.search(torch.from_numpy(xq[:1]), k)
+
+        # the reference's entry point: index_cpu_to_gpu_multiple(vres, vdev, index, co) with co.shard = False is
+        # Faiss's IndexReplicas -> inside a process group, a replica that answers its slice of the batch
+        import b200ivfpq as faiss
+
+        class _Whole:
+            nprobe = 5
+            d = 32
+            search = staticmethod(full_search)
+
+        co = faiss.GpuMultipleClonerOptions()
+        assert co.shard is False
+        cloned = faiss.index_cpu_to_gpu_multiple(None, None, _Whole(), co)
+        assert isinstance(cloned, DistributedIndexIVFPQ) and cloned.shard_mode == "replica" and not cloned.peer_merge
+        Dc, Ic = cloned.search(torch.from_numpy(xq[:23]), k)
+        assert torch.equal(Dc, Dr) and torch.equal(Ic, Ir)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), D=D.numpy(), I=I.numpy(), Dr=Dr.numpy(), Ir=Ir.numpy(),
                  D1=D1.numpy(), I1=I1.numpy())
     finally:
