@@ -16,7 +16,9 @@
  *          LUT_construction.hpp:180-209, ADC.hpp:75-99, priority_queue_L1.hpp:65-75.
  * Parity status: the LUT arithmetic is pinned by the reference's literal known-answer test
  * (LUT_construction_PE_D128_M32/src/host.cpp:44-109; tests/golden/lut_kat_d128_m32.npz).  The
- * end-to-end search result is "parity unpinned" against the Faiss binary: no runnable Faiss, no
+ * coarse stage is pinned against the reference's own cell-selection code run here (vendored hnswlib
+ * brute force, host.cpp:516-581, via oracle/ref_coarse_shim.cpp -> oracle/_ref/; tests/test_reference_coarse.py).
+ * The end-to-end search result is "parity unpinned" against the Faiss binary: no runnable Faiss, no
  * SIFT1B index.
  *
  * Arithmetic contract, fixed so that CPU and GPU agree bit for bit:

@@ -13,8 +13,10 @@ Two implementations of the same arithmetic contract (see ivfpq_oracle.c header, 
   cross-check the C file on small cases.
 
 Parity status: LUT arithmetic pinned by the reference's literal KAT
-(retrieval_accelerator/LUT_construction_PEs/LUT_construction_PE_D128_M32/src/host.cpp:44-109);
-end-to-end search "parity unpinned" against the Faiss binary (Faiss not installable here).
+(retrieval_accelerator/LUT_construction_PEs/LUT_construction_PE_D128_M32/src/host.cpp:44-109); coarse stage pinned
+against the reference's own CPU cell selection run here (``ref_coarse``: vendored hnswlib brute force, host.cpp:516-581,
+compiled into oracle/_ref/ from the headers under /root/reference); end-to-end search "parity unpinned" against the
+Faiss binary (Faiss not installable here).
 """
 from __future__ import annotations
 
@@ -39,6 +41,49 @@ def build(force: bool = False) -> str:
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _SO
+
+
+# ---- oracle/_ref: code OF THE REFERENCE run here (row a1 only) -------------------------------------------------------
+_REF_SO = os.path.join(_HERE, "_ref", "libref_coarse.so")
+REF_SRC = "/root/reference/Chameleon/retrieval_accelerator/entire_accelerator_final_SIFT_M32/src"
+_ref_lib = None
+
+
+def build_ref(force: bool = False):
+    """Compile oracle/_ref/libref_coarse.so: the reference's own coarse-quantizer code (its vendored hnswlib
+    BruteforceSearch, host.cpp:516-581) behind ref_coarse_shim.cpp, from the headers where they lie under
+    /root/reference.  Returns the library path, or None when the reference is not mounted and nothing was prebuilt
+    (the GPU box only ever uses the prebuilt file)."""
+    src = os.path.join(_HERE, "ref_coarse_shim.cpp")
+    have_ref = os.path.exists(os.path.join(REF_SRC, "hnswlib", "hnswlib.h"))
+    stale = not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < os.path.getmtime(src)
+    if have_ref and (force or stale):
+        subprocess.run(["make", "-C", _HERE, "-B", "ref"], check=True, capture_output=True)
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+def ref_coarse(xq, centroids, nprobe):
+    """The reference's CPU cell selection (hnswlib brute force + searchKnn): (dis, ids), rows ascending.  Distances come
+    from hnswlib's SIMD L2 (another summation order than the contract): equal to rounding, not bit for bit."""
+    global _ref_lib
+    if _ref_lib is None:
+        path = build_ref()
+        if path is None:
+            raise FileNotFoundError("oracle/_ref/libref_coarse.so not built (reference not mounted)")
+        _ref_lib = ctypes.CDLL(path)
+        _ref_lib.ref_coarse_bruteforce.restype = ctypes.c_int
+        _ref_lib.ref_coarse_bruteforce.argtypes = [ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int64, _f32p,
+                                                   ctypes.c_int, _i64p, _f32p]
+        _ref_lib.ref_coarse_simd.restype = ctypes.c_char_p
+    xq, centroids = _f32(xq), _f32(centroids)
+    nq, d = xq.shape
+    ids = np.empty((nq, nprobe), np.int64)
+    dis = np.empty((nq, nprobe), np.float32)
+    rc = _ref_lib.ref_coarse_bruteforce(centroids.shape[0], d, _p(centroids, _f32p), nq, _p(xq, _f32p), nprobe,
+                                        _p(ids, _i64p), _p(dis, _f32p))
+    if rc:
+        raise RuntimeError(f"ref_coarse_bruteforce failed: {rc}")
+    return dis, ids
 
 
 def _f32(a):

@@ -63,3 +63,22 @@ def assert_same_modulo_ties(D, I, D_ref, I_ref, what=""):
             if a != b:
                 assert j == k - 1, f"{what}: query {q} ids differ outside a boundary tie: {I[q]} vs {I_ref[q]}"
             i = j + 1
+
+
+def assert_same_modulo_near_ties(D, I, D_ref, I_ref, rtol, what=""):
+    """For comparisons against code that sums in another order (the reference's SIMD kernels): the sorted distance
+    profiles agree within `rtol`, and wherever the ids differ the two entries involved are a near tie -- their distances
+    differ by at most 2*rtol relative (an order swap), or the missing entry sat within 2*rtol of the k-th distance."""
+    D, D_ref = np.asarray(D, np.float32), np.asarray(D_ref, np.float32)
+    np.testing.assert_allclose(D, D_ref, rtol=rtol, atol=0, err_msg=what + " distances")
+    nq, k = D.shape
+    for q in range(nq):
+        if np.array_equal(I[q], I_ref[q]):
+            continue
+        mine = {int(i): p for p, i in enumerate(I[q])}
+        for pos in np.nonzero(I[q] != I_ref[q])[0]:
+            other = int(I_ref[q, pos])
+            d_here = float(D_ref[q, pos])
+            d_there = float(D[q, mine[other]]) if other in mine else float(D[q, k - 1])
+            assert abs(d_there - d_here) <= 2 * rtol * max(d_here, 1e-30), \
+                f"{what}: query {q} position {pos}: id {other} vs {int(I[q, pos])} is not a near tie"
