@@ -17,7 +17,9 @@
  * Parity status: the LUT arithmetic is pinned by the reference's literal known-answer test
  * (LUT_construction_PE_D128_M32/src/host.cpp:44-109; tests/golden/lut_kat_d128_m32.npz).  The
  * coarse stage is pinned against the reference's own cell-selection code run here (vendored hnswlib
- * brute force, host.cpp:516-581, via oracle/ref_coarse_shim.cpp -> oracle/_ref/; tests/test_reference_coarse.py).
+ * brute force, host.cpp:516-581, via oracle/ref_coarse_shim.cpp -> oracle/_ref/; tests/test_reference_coarse.py),
+ * and the LUT / ADC arithmetic against the reference's HLS kernels (LUT_construction.hpp, ADC.hpp) run as a C
+ * simulation (oracle/ref_fpga_shim.cpp; bit for bit, tests/test_reference_fpga_kernels.py).
  * The end-to-end search result is "parity unpinned" against the Faiss binary: no runnable Faiss, no
  * SIFT1B index.
  *

@@ -15,7 +15,8 @@ Two implementations of the same arithmetic contract (see ivfpq_oracle.c header, 
 Parity status: LUT arithmetic pinned by the reference's literal KAT
 (retrieval_accelerator/LUT_construction_PEs/LUT_construction_PE_D128_M32/src/host.cpp:44-109); coarse stage pinned
 against the reference's own CPU cell selection run here (``ref_coarse``: vendored hnswlib brute force, host.cpp:516-581,
-compiled into oracle/_ref/ from the headers under /root/reference); end-to-end search "parity unpinned" against the
+compiled into oracle/_ref/ from the headers under /root/reference); LUT and ADC arithmetic pinned bit for bit against
+the reference's HLS kernels run as a C simulation (``ref_fpga_lut_adc``); end-to-end search "parity unpinned" against the
 Faiss binary (Faiss not installable here).
 """
 from __future__ import annotations
@@ -50,13 +51,15 @@ _ref_lib = None
 
 
 def build_ref(force: bool = False):
-    """Compile oracle/_ref/libref_coarse.so: the reference's own coarse-quantizer code (its vendored hnswlib
-    BruteforceSearch, host.cpp:516-581) behind ref_coarse_shim.cpp, from the headers where they lie under
-    /root/reference.  Returns the library path, or None when the reference is not mounted and nothing was prebuilt
+    """Compile oracle/_ref/: the reference's own coarse-quantizer code (its vendored hnswlib BruteforceSearch,
+    host.cpp:516-581) behind ref_coarse_shim.cpp, and its HLS LUT-construction / ADC kernels as a C simulation behind
+    ref_fpga_shim.cpp, from the sources where they lie under /root/reference.  Returns the library path, or None when the reference is not mounted and nothing was prebuilt
     (the GPU box only ever uses the prebuilt file)."""
-    src = os.path.join(_HERE, "ref_coarse_shim.cpp")
     have_ref = os.path.exists(os.path.join(REF_SRC, "hnswlib", "hnswlib.h"))
-    stale = not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < os.path.getmtime(src)
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in
+                 ("ref_coarse_shim.cpp", "ref_fpga_shim.cpp", "hls_csim/ap_int.h", "hls_csim/hls_stream.h", "Makefile"))
+    built = [_REF_SO] + [os.path.join(_HERE, "_ref", f"libref_fpga_{v}.so") for v in FPGA_VARIANTS]
+    stale = any(not os.path.exists(b) or os.path.getmtime(b) < newest for b in built)
     if have_ref and (force or stale):
         subprocess.run(["make", "-C", _HERE, "-B", "ref"], check=True, capture_output=True)
     return _REF_SO if os.path.exists(_REF_SO) else None
@@ -84,6 +87,45 @@ def ref_coarse(xq, centroids, nprobe):
     if rc:
         raise RuntimeError(f"ref_coarse_bruteforce failed: {rc}")
     return dis, ids
+
+
+FPGA_VARIANTS = {"SIFT_M16": (128, 16), "SIFT_M32": (128, 32), "Deep_M16": (96, 16), "Deep_M32": (96, 32)}
+_fpga_libs = {}
+
+
+def ref_fpga_lut_adc(variant, pq, xq, centers, nscan, codes):
+    """The reference's OWN HLS kernels (LUT_construction.hpp: LUT_construction_wrapper; ADC.hpp: PQ_lookup_computation of
+    retrieval_accelerator/entire_accelerator_final_<variant>/src) run as a C simulation (ref_fpga_shim.cpp).
+    pq (M, 256, dsub); xq (nq, D); centers (nq, nprobe, D) = the probed cells' centroids; nscan (nq, nprobe) entries
+    scanned per cell; codes (sum nscan, M) in (query, probe, entry) order.
+    Returns (lut (nq, nprobe, M, 256), dist (sum nscan,))."""
+    D, M = FPGA_VARIANTS[variant]
+    if variant not in _fpga_libs:
+        if build_ref() is None or not os.path.exists(os.path.join(_HERE, "_ref", f"libref_fpga_{variant}.so")):
+            raise FileNotFoundError(f"oracle/_ref/libref_fpga_{variant}.so not built (reference not mounted)")
+        lib = ctypes.CDLL(os.path.join(_HERE, "_ref", f"libref_fpga_{variant}.so"))
+        d_, m_ = ctypes.c_int(), ctypes.c_int()
+        lib.ref_fpga_dims(ctypes.byref(d_), ctypes.byref(m_))
+        assert (d_.value, m_.value) == (D, M), "constants.hpp of the variant changed"
+        lib.ref_fpga_lut_adc.restype = ctypes.c_int
+        lib.ref_fpga_lut_adc.argtypes = [ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, ctypes.POINTER(ctypes.c_int),
+                                         _u8p, _f32p, _f32p]
+        _fpga_libs[variant] = lib
+    lib = _fpga_libs[variant]
+    pq, xq, centers = _f32(pq), _f32(xq), _f32(centers)
+    nscan = np.ascontiguousarray(nscan, np.int32)
+    codes = _u8(codes).reshape(-1, M)
+    nq, nprobe = nscan.shape
+    assert pq.shape == (M, 256, D // M) and xq.shape == (nq, D) and centers.shape == (nq, nprobe, D)
+    assert codes.shape[0] == int(nscan.sum())
+    lut = np.empty((nq, nprobe, 256, M), np.float32)
+    dist = np.empty(codes.shape[0], np.float32)
+    rc = lib.ref_fpga_lut_adc(nq, nprobe, _p(pq, _f32p), _p(xq, _f32p), _p(centers, _f32p),
+                              nscan.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(codes, _u8p), _p(lut, _f32p),
+                              _p(dist, _f32p))
+    if rc:
+        raise RuntimeError(f"ref_fpga_lut_adc failed: {rc}")
+    return np.ascontiguousarray(lut.transpose(0, 1, 3, 2)), dist
 
 
 def _f32(a):
