@@ -93,12 +93,7 @@ FPGA_VARIANTS = {"SIFT_M16": (128, 16), "SIFT_M32": (128, 32), "Deep_M16": (96, 
 _fpga_libs = {}
 
 
-def ref_fpga_lut_adc(variant, pq, xq, centers, nscan, codes):
-    """The reference's OWN HLS kernels (LUT_construction.hpp: LUT_construction_wrapper; ADC.hpp: PQ_lookup_computation of
-    retrieval_accelerator/entire_accelerator_final_<variant>/src) run as a C simulation (ref_fpga_shim.cpp).
-    pq (M, 256, dsub); xq (nq, D); centers (nq, nprobe, D) = the probed cells' centroids; nscan (nq, nprobe) entries
-    scanned per cell; codes (sum nscan, M) in (query, probe, entry) order.
-    Returns (lut (nq, nprobe, M, 256), dist (sum nscan,))."""
+def _fpga_lib(variant):
     D, M = FPGA_VARIANTS[variant]
     if variant not in _fpga_libs:
         if build_ref() is None or not os.path.exists(os.path.join(_HERE, "_ref", f"libref_fpga_{variant}.so")):
@@ -110,8 +105,36 @@ def ref_fpga_lut_adc(variant, pq, xq, centers, nscan, codes):
         lib.ref_fpga_lut_adc.restype = ctypes.c_int
         lib.ref_fpga_lut_adc.argtypes = [ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, ctypes.POINTER(ctypes.c_int),
                                          _u8p, _f32p, _f32p]
+        lib.ref_fpga_queue_l1.restype = ctypes.c_int
+        lib.ref_fpga_queue_l1.argtypes = [ctypes.c_int, ctypes.c_int, _f32p, ctypes.POINTER(ctypes.c_int), _f32p]
         _fpga_libs[variant] = lib
-    lib = _fpga_libs[variant]
+    return _fpga_libs[variant]
+
+
+def ref_fpga_queue(dist, k, variant="SIFT_M16"):
+    """The reference's systolic priority queue (priority_queue_L1.hpp, queue length k in {1, 10, 100}) fed the
+    candidates `dist` in scan order.  Returns (offsets, distances) of the occupied slots sorted by (distance, offset)."""
+    dist = _f32(dist)
+    off = np.empty(k, np.int32)
+    od = np.empty(k, np.float32)
+    rc = _fpga_lib(variant).ref_fpga_queue_l1(k, dist.shape[0], _p(dist, _f32p),
+                                              off.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(od, _f32p))
+    if rc:
+        raise ValueError(f"queue length {k} not instantiated (1, 10, 100)")
+    keep = od < np.float32(9e9)                      # LARGE_NUM marks an empty slot
+    off, od = off[keep], od[keep]
+    order = np.lexsort((off, od))
+    return off[order].astype(np.int64), od[order]
+
+
+def ref_fpga_lut_adc(variant, pq, xq, centers, nscan, codes):
+    """The reference's OWN HLS kernels (LUT_construction.hpp: LUT_construction_wrapper; ADC.hpp: PQ_lookup_computation of
+    retrieval_accelerator/entire_accelerator_final_<variant>/src) run as a C simulation (ref_fpga_shim.cpp).
+    pq (M, 256, dsub); xq (nq, D); centers (nq, nprobe, D) = the probed cells' centroids; nscan (nq, nprobe) entries
+    scanned per cell; codes (sum nscan, M) in (query, probe, entry) order.
+    Returns (lut (nq, nprobe, M, 256), dist (sum nscan,))."""
+    D, M = FPGA_VARIANTS[variant]
+    lib = _fpga_lib(variant)
     pq, xq, centers = _f32(pq), _f32(xq), _f32(centers)
     nscan = np.ascontiguousarray(nscan, np.int32)
     codes = _u8(codes).reshape(-1, M)

@@ -3,6 +3,11 @@
 // Runs the REFERENCE'S OWN HLS kernels for rows a2-a4 of the hot path as a C simulation:
 //   LUT_construction.hpp : LUT_construction_wrapper  (residual q - c, T[m][k] = sum_j (r_j - pq[m][k][j])^2)
 //   ADC.hpp              : PQ_lookup_computation      (dist = sum_{b<M} LUT[b][code[b]], b ascending from 0)
+// and, for the selection rule of row a5,
+//   priority_queue_L1.hpp: Priority_queue_L1<PQ_out_t, k, Collect_smallest>::insert_wrapper -- the systolic queue whose
+//                          compare_swap (:65-75) moves an entry only past a strictly larger one.  (The accelerator's
+//                          full hierarchy truncates its L1 queues and is approximate -- constants.hpp:23-31 -- which is
+//                          why only the single queue, fed every candidate, is used here.)
 // of retrieval_accelerator/entire_accelerator_final_<DATASET>_M<m>/src, included from where they lie under
 // /root/reference (oracle/Makefile passes -I; D and M come from that directory's constants.hpp).  Nothing of the
 // reference is copied.  Xilinx's <ap_int.h> / <hls_stream.h> are not installed here; oracle/hls_csim/ holds our own
@@ -13,6 +18,7 @@
 
 #include "LUT_construction.hpp"
 #include "ADC.hpp"
+#include "priority_queue_L1.hpp"
 
 namespace {
 void push_vector_512(hls::stream<ap_uint<512> >& s, const float* v) {
@@ -73,4 +79,38 @@ int ref_fpga_lut_adc(int nq, int nprobe, const float* pq, const float* xq, const
     }
     for (long i = 0; i < total; i++) dist[i] = s_res.read().dist;
     return (s_lut.empty() && s_codes.empty() && s_res.empty()) ? 0 : -1;
+}
+
+namespace {
+template <int QS>
+void run_queue(int n, const float* dist, int* out_off, float* out_dist) {
+    hls::stream<int> s_iter;
+    hls::stream<PQ_out_t> s_in, s_out;
+    s_iter.write(n);
+    for (int i = 0; i < n; i++) {
+        PQ_out_t e;
+        e.cell_ID = 0;
+        e.offset = i;          // scan order
+        e.dist = dist[i];
+        s_in.write(e);
+    }
+    Priority_queue_L1<PQ_out_t, QS, Collect_smallest> queue;
+    queue.insert_wrapper(1, s_iter, s_in, s_out);
+    for (int i = 0; i < QS; i++) {          // queue order, not sorted; unfilled slots keep dist = LARGE_NUM
+        const PQ_out_t e = s_out.read();
+        out_off[i] = e.offset;
+        out_dist[i] = e.dist;
+    }
+}
+}  // namespace
+
+// The reference's queue of length k (1, 10 or 100) fed n candidates in scan order; returns its k slots.
+extern "C" __attribute__((visibility("default")))
+int ref_fpga_queue_l1(int k, int n, const float* dist, int* out_off, float* out_dist) {
+    switch (k) {
+        case 1: run_queue<1>(n, dist, out_off, out_dist); return 0;
+        case 10: run_queue<10>(n, dist, out_off, out_dist); return 0;
+        case 100: run_queue<100>(n, dist, out_off, out_dist); return 0;
+        default: return -1;
+    }
 }

@@ -117,3 +117,74 @@ def test_cuda_search_returns_the_reference_kernels_distances(ref, variant):
         index.set_lists(c["offsets"], c["codes"], c["ids"])
         return index.search_preassigned(c["xq"], k, c["probes"])
     _check_search_against_reference_kernels(ref, variant, run)
+
+
+# ---- row a5: the selection rule, against the reference's own queue ------------------------------------------------
+def _tie_case(oracle, variant, seed, n=400, distinct=6, nq=12, nlist=8):
+    """ONE populated cell (the others are empty) whose entries repeat a handful of distinct codes: every query sees long
+    runs of EXACTLY equal distances, so which entries make the top-k is decided by the tie rule alone."""
+    D, M = oracle.FPGA_VARIANTS[variant]
+    rng = np.random.default_rng(seed)
+    pq = (rng.standard_normal((M, 256, D // M)) * 0.3).astype(np.float32)
+    cent = rng.random((nlist, D), dtype=np.float32)
+    xq = rng.random((nq, D), dtype=np.float32)
+    rows = rng.integers(0, 256, (distinct, M), dtype=np.uint8)
+    codes = rows[rng.integers(0, distinct, n)]
+    offsets = np.full(nlist + 1, n, np.int64)
+    offsets[0] = 0                                               # everything lives in cell 0
+    return dict(D=D, M=M, pq=pq, cent=cent, xq=xq, offsets=offsets, codes=codes,
+                ids=np.arange(n, dtype=np.int64), probes=np.zeros((nq, 1), np.int64))
+
+
+def _check_selection_against_reference_queue(ref, variant, k, search_preassigned):
+    """Reference chain, all its own code: HLS LUT -> HLS ADC -> systolic queue of length k (strict `<`,
+    priority_queue_L1.hpp:65-75) fed in scan order.  The search must return the same k entries: with ids = scan
+    positions, the same ids in the same (distance, scan order) ranking, the same distance bits."""
+    c = _tie_case(ref, variant, seed=3 + k)
+    n = c["codes"].shape[0]
+    nq = c["xq"].shape[0]
+    _, dist = ref.ref_fpga_lut_adc(variant, c["pq"], c["xq"], c["cent"][c["probes"]], np.full((nq, 1), n, np.int32),
+                                   np.tile(c["codes"], (nq, 1)))
+    D, I = search_preassigned(c, k)
+    for q in range(nq):
+        dq = dist[q * n:(q + 1) * n]
+        assert np.unique(dq).shape[0] <= 6, "the case is built from at most six distinct distances"
+        off, od = ref.ref_fpga_queue(dq, k, variant)
+        assert off.shape[0] == min(k, n)
+        assert np.array_equal(np.asarray(I[q, :off.shape[0]]), off), f"{variant} k={k} q{q}: selected entries differ"
+        _util.assert_bit_equal(np.asarray(D[q, :off.shape[0]], np.float32), od, f"{variant} k={k} q{q}: distances")
+
+
+@pytest.mark.parametrize("k", [1, 10, 100])
+@pytest.mark.parametrize("variant", ["SIFT_M16", "Deep_M16", "SIFT_M32"])
+def test_oracle_tie_rule_is_the_references_queue(ref, variant, k):
+    def run(c, kk):
+        return ref.C.search_preassigned(c["xq"], c["cent"], c["pq"], c["offsets"], c["codes"], c["ids"], c["probes"], kk)
+    _check_selection_against_reference_queue(ref, variant, k, run)
+
+
+def test_reference_queue_is_exact_under_heavy_ties(ref):
+    """The systolic queue by itself against the rule it is taken to implement: the k smallest under the total order
+    (distance, scan order) -- among equal distances the earlier-scanned entry stays."""
+    rng = np.random.default_rng(0)
+    for k in (1, 10, 100):
+        for n, levels in [(5, 3), (50, 8), (500, 20), (3000, 50), (3000, 100000)]:
+            d = (rng.integers(0, levels, n) / levels).astype(np.float32)
+            off, od = ref.ref_fpga_queue(d, k)
+            want = np.lexsort((np.arange(n), d))[:k]
+            assert np.array_equal(off, want), (k, n, levels)
+            _util.assert_bit_equal(od, d[want], "queue distances")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 10, 100])
+@pytest.mark.parametrize("variant", ["SIFT_M16", "Deep_M16", "SIFT_M32"])
+def test_cuda_tie_rule_is_the_references_queue(ref, variant, k):
+    import b200ivfpq as faiss
+
+    def run(c, kk):
+        index = faiss.IndexIVFPQ(faiss.IndexFlatL2(c["D"]), c["D"], c["cent"].shape[0], c["M"], 8)
+        index.set_codebooks(c["cent"], c["pq"])
+        index.set_lists(c["offsets"], c["codes"], c["ids"])
+        return index.search_preassigned(c["xq"], kk, c["probes"])
+    _check_selection_against_reference_queue(ref, variant, k, run)
