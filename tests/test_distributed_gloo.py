@@ -91,6 +91,106 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+class _OracleQuantizer:
+    """index.quantizer stand-in on CPU tensors: the oracle's coarse stage."""
+
+    def __init__(self, oracle, cent):
+        self.oracle, self.cent, self.calls = oracle, cent, []
+
+    def search(self, x, k):
+        self.calls.append(int(x.shape[0]))
+        D, I = self.oracle.C.coarse(x.numpy(), self.cent, k)
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+
+class _OracleShard:
+    """Rank-local IndexIVFPQ stand-in: quantizer.search / search / search_preassigned answered by the oracle on this
+    rank's shard.  Lets DistributedIndexIVFPQ._local_search itself (sliced coarse stage, probe exchange, by-list probe
+    masking) run under gloo; only the merge kernel is injected."""
+
+    def __init__(self, oracle, a, off, codes, ids, nprobe):
+        self.oracle, self.a, self.off, self.codes, self.ids = oracle, a, off, codes, ids
+        self.nprobe, self.d, self.nlist = nprobe, a["coarse"].shape[1], a["coarse"].shape[0]
+        self.quantizer = _OracleQuantizer(oracle, a["coarse"])
+        self.preassigned = []
+
+    def search(self, x, k):
+        D, I = self.oracle.C.search(x.numpy(), self.a["coarse"], self.a["pq"], self.off, self.codes, self.ids,
+                                    self.nprobe, k)
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+    def search_preassigned(self, x, k, probes):
+        self.preassigned.append(probes.clone())
+        D, I = self.oracle.C.search_preassigned(x.numpy(), self.a["coarse"], self.a["pq"], self.off, self.codes,
+                                                self.ids, probes.numpy(), k)
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def _worker_local_search(rank, world, port, out_dir):
+    """vector and list layouts through the REAL _local_search (no local_search_fn injection)."""
+    for p in (ROOT, os.path.join(ROOT, "chameleon-rag-acceleration_b200"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    from oracle import ivfpq_oracle as oracle
+    from b200ivfpq.shards import DistributedIndexIVFPQ
+    import _util as U
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a = U.make_index_arrays(oracle, 17, 32, 16, 8, 3000, id_scramble=False)
+        xq = torch.from_numpy(U.make_queries(6, a, 24))
+        nprobe, k, nlist = 5, 10, 16
+        sizes = np.diff(a["offsets"])
+        list_no = np.repeat(np.arange(nlist), sizes)
+
+        def merge(Ds, Is):
+            D, I = oracle.C.merge_shards(Ds.numpy(), Is.numpy())
+            return torch.from_numpy(D), torch.from_numpy(I)
+
+        out = {}
+        for mode in ("vector", "list"):
+            keep = ((a["ids"] % world) == rank) if mode == "vector" else ((list_no % world) == rank)
+            off = np.zeros(nlist + 1, np.int64)
+            off[1:] = np.cumsum(np.bincount(list_no[keep], minlength=nlist))
+            local = _OracleShard(oracle, a, off, a["codes"][keep], a["ids"][keep], nprobe)
+            index = DistributedIndexIVFPQ(local, merge_fn=merge, shard_mode=mode)
+            assert not index.peer_merge
+            D, I = index.search(xq, k)                       # 24 queries >= 8 * world: the coarse stage is sliced
+            assert local.quantizer.calls == [12], "each rank ranks the centroids for its half of the batch only"
+            probes = local.preassigned[0]
+            assert probes.shape == (24, nprobe)
+            if mode == "list":
+                own = probes >= 0
+                assert bool(((probes[own] % world) == rank).all()) and bool((~own).any()), "foreign lists masked"
+            D3, I3 = index.search(xq[:3], k)                 # 3 queries < 8 * world: no slicing
+            if mode == "vector":
+                assert local.quantizer.calls == [12]         # plain local search, quantizer not called separately
+            else:
+                assert local.quantizer.calls == [12, 3]      # by-list always needs the probes to mask them
+            out[mode] = (D.numpy(), I.numpy(), D3.numpy(), I3.numpy())
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{f"{m}_{n}": v for m, t in out.items()
+                                                              for n, v in zip(("D", "I", "D3", "I3"), t)})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world2_sliced_coarse_and_by_list_masking(oracle, tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker_local_search, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a = _util.make_index_arrays(oracle, 17, 32, 16, 8, 3000, id_scramble=False)
+    xq = _util.make_queries(6, a, 24)
+    D, I = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 5, 10)
+    outs = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    for mode in ("vector", "list"):
+        for r in range(world):
+            _util.assert_same_modulo_ties(outs[r][f"{mode}_D"], outs[r][f"{mode}_I"], D, I, f"{mode} rank {r}")
+            _util.assert_same_modulo_ties(outs[r][f"{mode}_D3"], outs[r][f"{mode}_I3"], D[:3], I[:3],
+                                          f"{mode} small batch rank {r}")
+
+
 def _worker_rxs(rank, world, port, out_dir):
     """2 replicas x 2 shards (the reference's `-R 2` on 4 GPUs, bench_gpu_performance_OSDI.py:613-626)."""
     for p in (ROOT, os.path.join(ROOT, "chameleon-rag-acceleration_b200"), os.path.join(ROOT, "tests")):
