@@ -19,7 +19,8 @@
  * coarse stage is pinned against the reference's own cell-selection code run here (vendored hnswlib
  * brute force, host.cpp:516-581, via oracle/ref_coarse_shim.cpp -> oracle/_ref/; tests/test_reference_coarse.py),
  * and the LUT / ADC arithmetic against the reference's HLS kernels (LUT_construction.hpp, ADC.hpp) run as a C
- * simulation (oracle/ref_fpga_shim.cpp; bit for bit, tests/test_reference_fpga_kernels.py).
+ * simulation (oracle/ref_fpga_shim.cpp; bit for bit, tests/test_reference_fpga_kernels.py), and the whole search against
+ * the reference's host + complete accelerator kernel (oracle/ref_accel_shim.cpp; tests/test_reference_system.py).
  * The end-to-end search result is "parity unpinned" against the Faiss binary: no runnable Faiss, no
  * SIFT1B index.
  *

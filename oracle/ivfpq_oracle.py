@@ -16,7 +16,8 @@ Parity status: LUT arithmetic pinned by the reference's literal KAT
 (retrieval_accelerator/LUT_construction_PEs/LUT_construction_PE_D128_M32/src/host.cpp:44-109); coarse stage pinned
 against the reference's own CPU cell selection run here (``ref_coarse``: vendored hnswlib brute force, host.cpp:516-581,
 compiled into oracle/_ref/ from the headers under /root/reference); LUT and ADC arithmetic pinned bit for bit against
-the reference's HLS kernels run as a C simulation (``ref_fpga_lut_adc``); end-to-end search "parity unpinned" against the
+the reference's HLS kernels run as a C simulation (``ref_fpga_lut_adc``), and the whole search against the reference's
+complete accelerator kernel (``ref_accel_search``); end-to-end search "parity unpinned" against the
 Faiss binary (Faiss not installable here).
 """
 from __future__ import annotations
@@ -57,8 +58,10 @@ def build_ref(force: bool = False):
     (the GPU box only ever uses the prebuilt file)."""
     have_ref = os.path.exists(os.path.join(REF_SRC, "hnswlib", "hnswlib.h"))
     newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in
-                 ("ref_coarse_shim.cpp", "ref_fpga_shim.cpp", "hls_csim/ap_int.h", "hls_csim/hls_stream.h", "Makefile"))
-    built = [_REF_SO] + [os.path.join(_HERE, "_ref", f"libref_fpga_{v}.so") for v in FPGA_VARIANTS]
+                 ("ref_coarse_shim.cpp", "ref_fpga_shim.cpp", "ref_accel_shim.cpp", "hls_csim/ap_int.h",
+                  "hls_csim/hls_stream.h", "Makefile"))
+    built = [_REF_SO] + [os.path.join(_HERE, "_ref", f"libref_{kind}_{v}.so") for v in FPGA_VARIANTS
+                         for kind in ("fpga", "accel")]
     stale = any(not os.path.exists(b) or os.path.getmtime(b) < newest for b in built)
     if have_ref and (force or stale):
         subprocess.run(["make", "-C", _HERE, "-B", "ref"], check=True, capture_output=True)
@@ -125,6 +128,101 @@ def ref_fpga_queue(dist, k, variant="SIFT_M16"):
     off, od = off[keep], od[keep]
     order = np.lexsort((off, od))
     return off[order].astype(np.int64), od[order]
+
+
+_accel_libs = {}
+
+
+def ref_accel_dims(variant):
+    """(D, M, TOPK, ADC_PE_NUM, PRIORITY_QUEUE_LEN_L1) the accelerator build was compiled with (its constants.hpp)."""
+    if variant not in _accel_libs:
+        path = os.path.join(_HERE, "_ref", f"libref_accel_{variant}.so")
+        if build_ref() is None or not os.path.exists(path):
+            raise FileNotFoundError(f"oracle/_ref/libref_accel_{variant}.so not built (reference not mounted)")
+        lib = ctypes.CDLL(path)
+        lib.ref_accel_run.restype = None
+        lib.ref_accel_run.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 11
+        _accel_libs[variant] = lib
+    v = [ctypes.c_int() for _ in range(5)]
+    _accel_libs[variant].ref_accel_dims(*[ctypes.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+def ref_accel_search(variant, centroids, pq, offsets, codes, ids, xq, probes):
+    """The reference's COMPLETE accelerator kernel (`vadd`, retrieval_accelerator/entire_accelerator_final_<variant>/src/
+    vadd.cpp) run as a C simulation on the probed cells `probes` (nq, nprobe): returns (D, I) of shape (nq, TOPK) sorted
+    by (distance, id); TOPK = 100 is a compile-time constant of the reference.
+
+    This function is the HOST SIDE, written here from the formats the kernel parses (the reference's host.cpp needs the
+    Xilinx runtime and is not used):
+      * meta_data_init (vadd.cpp load_meta_data / DRAM_utils.hpp:185-222): per cell the PQ-code start word, the vector-id
+        start index, the cell size; then the PQ codebook (M, 256, D/M) as raw floats;
+      * PQ codes (DRAM_utils.hpp:103-183, load_PQ_codes): four banks of 512-bit words; vector j of a cell is entry
+        j // ADC_PE_NUM of PE s = j % ADC_PE_NUM, i.e. bank s // lanes, lane a = s % lanes (lanes = ADC_PE_NUM / 4),
+        bytes [a*M, (a+1)*M) of that bank's word `start + entry`;
+      * vector ids (hierarchical_priority_queue.hpp:185-263): bank b, index `vid_start + entry * lanes + a`;
+      * query packets (vadd.cpp:38-97, network_input_processing): header word (query id, nprobe), cell ids, the query,
+        the nprobe centroids, all in 512-bit words, zero padded;
+      * results (vadd.cpp:99-160): header word, TOPK 64-bit ids, TOPK fp32 distances.
+    The accelerator is approximate by design (its first-level queues keep PRIORITY_QUEUE_LEN_L1 entries each); callers
+    pick inputs on which that truncation does not bite, and every first-level queue must receive at least that many
+    candidates per query (empty queue slots carry uninitialised cell ids in the reference's code)."""
+    D, M, TOPK, PE, L1 = ref_accel_dims(variant)
+    lib = _accel_libs[variant]
+    centroids, pq, xq = _f32(centroids), _f32(pq), _f32(xq)
+    codes, ids, offsets = _u8(codes).reshape(-1, M), _i64(ids), _i64(offsets)
+    probes = np.ascontiguousarray(probes, np.int64)
+    assert pq.shape == (M, 256, D // M) and centroids.shape[1] == D and xq.shape[1] == D
+    lanes = PE // 4
+    nlist = offsets.shape[0] - 1
+    sizes = np.diff(offsets)
+    words = (sizes + PE - 1) // PE
+    pq_start = np.zeros(nlist, np.int64)
+    pq_start[1:] = np.cumsum(words)[:-1]
+    vid_start = pq_start * lanes
+    nq, nprobe = probes.shape
+    per_query = sizes[probes].sum(axis=1)
+    if per_query.min() < 4 * PE * L1:
+        raise ValueError("every query must scan enough vectors to fill all first-level queues of the accelerator")
+    total_words = max(int(words.sum()), 1)
+    bank_codes = np.zeros((4, total_words, 64), np.uint8)
+    bank_ids = np.zeros((4, total_words * lanes), np.uint64)
+    list_no = np.repeat(np.arange(nlist), sizes)
+    j = np.arange(codes.shape[0]) - offsets[list_no]              # position inside the cell
+    entry, s = j // PE, j % PE
+    bank, lane = s // lanes, s % lanes
+    word = pq_start[list_no] + entry
+    bank_codes.reshape(4, total_words, 64 // M, M)[bank, word, lane] = codes
+    bank_ids[bank, vid_start[list_no] + entry * lanes + lane] = ids.astype(np.uint64)
+    meta = np.ascontiguousarray(np.concatenate([pq_start.astype(np.int32), vid_start.astype(np.int32),
+                                                sizes.astype(np.int32), pq.reshape(-1).view(np.int32)]))
+    wvec = (D * 4 + 63) // 64
+    wcell = (nprobe * 4 + 63) // 64
+    packets = np.zeros((nq, 1 + wcell + wvec + nprobe * wvec, 16), np.int32)
+    packets[:, 0, 0] = np.arange(nq)
+    packets[:, 0, 1] = nprobe
+    cells = np.zeros((nq, wcell * 16), np.int32)
+    cells[:, :nprobe] = probes
+    packets[:, 1:1 + wcell] = cells.reshape(nq, wcell, 16)
+    vec = np.zeros((nq, wvec * 16), np.float32)
+    vec[:, :D] = xq
+    packets[:, 1 + wcell:1 + wcell + wvec] = vec.view(np.int32).reshape(nq, wvec, 16)
+    cen = np.zeros((nq, nprobe, wvec * 16), np.float32)
+    cen[:, :, :D] = centroids[probes]
+    packets[:, 1 + wcell + wvec:] = cen.view(np.int32).reshape(nq, nprobe * wvec, 16)
+    wid, wdist = (TOPK * 8 + 63) // 64, (TOPK * 4 + 63) // 64
+    out = np.zeros((nq, 1 + wid + wdist, 64), np.uint8)
+    lib.ref_accel_run(nq, nlist, nprobe, meta.ctypes.data, packets.ctypes.data,
+                      *[bank_codes[b].ctypes.data for b in range(4)], *[bank_ids[b].ctypes.data for b in range(4)],
+                      out.ctypes.data)
+    I = np.empty((nq, TOPK), np.int64)
+    Dist = np.empty((nq, TOPK), np.float32)
+    for q in range(nq):
+        iq = out[q, 1:1 + wid].reshape(-1).view(np.uint64)[:TOPK].astype(np.int64)
+        dq = out[q, 1 + wid:].reshape(-1).view(np.float32)[:TOPK]
+        order = np.lexsort((iq, dq))
+        I[q], Dist[q] = iq[order], dq[order]
+    return Dist, I
 
 
 def ref_fpga_lut_adc(variant, pq, xq, centers, nscan, codes):

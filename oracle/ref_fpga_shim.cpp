@@ -28,7 +28,7 @@ void push_vector_512(hls::stream<ap_uint<512> >& s, const float* v) {
         float lane[16];
         for (int j = 0; j < 16; j++) lane[j] = (i * 16 + j < D) ? v[i * 16 + j] : 0.0f;
         ap_uint<512> reg;
-        std::memcpy(reg.w, lane, 64);
+        std::memcpy(reg.b, lane, 64);
         s.write(reg);
     }
 }
