@@ -98,3 +98,27 @@ def test_server_with_a_real_index(oracle):
     Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 4, 10)
     _util.assert_bit_equal(out["dist"], Dr, "D over the wire")
     _util.assert_bit_equal(out["id"], Ir, "I over the wire")
+
+
+def test_wire_bytes_equal_the_references_encoders():
+    """tests/golden/wire_format.npz was produced by RUNNING the reference's serialization_utils.py
+    (tests/golden/make_wire_golden.py): our encoders must emit exactly its bytes and our decoders must read its bytes
+    back to the inputs."""
+    from b200ivfpq import server as w
+    g = np.load(os.path.join(ROOT, "tests", "golden", "wire_format.npz"))
+    for tag in ("a", "b", "c"):
+        batch, dim, nprobe, k = (int(v) for v in g[f"{tag}_shape"])
+        q, lists, I, D = g[f"{tag}_q"], g[f"{tag}_lists"], g[f"{tag}_I"], g[f"{tag}_D"]
+        req, reql, ans = g[f"{tag}_req"].tobytes(), g[f"{tag}_req_lists"].tobytes(), g[f"{tag}_ans"].tobytes()
+        assert bytes(w.encode_request(q, k)) == req, tag
+        assert bytes(w.encode_request_with_lists(q, lists, k)) == reql, tag
+        assert bytes(w.encode_answer(I, D)) == ans, tag
+        k2, q2 = w.decode_request(req, batch, dim)
+        assert k2 == k and np.array_equal(q2, q)
+        k3, q3, l3 = w.decode_request_with_lists(reql, batch, dim, nprobe)
+        assert k3 == k and np.array_equal(q3, q) and np.array_equal(l3, lists)
+        I2, D2 = w.decode_answer(ans, k, batch)
+        assert np.array_equal(I2, I) and np.array_equal(D2, D)
+        assert w.request_message_length(batch, dim) == len(req)
+        assert w.request_message_length_with_lists(batch, dim, nprobe) == len(reql)
+        assert w.answer_message_len(k, batch) == len(ans)
