@@ -122,3 +122,58 @@ def test_wire_bytes_equal_the_references_encoders():
         assert w.request_message_length(batch, dim) == len(req)
         assert w.request_message_length_with_lists(batch, dim, nprobe) == len(reql)
         assert w.answer_message_len(k, batch) == len(ans)
+
+
+REF_RALM = "/root/reference/Chameleon/llm_inference_gpu"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_RALM, "ralm", "retriever", "retriever.py")),
+                    reason="the reference is only mounted in the build container")
+@pytest.mark.parametrize("with_lists", [False, True])
+def test_the_references_own_client_talks_to_our_server(with_lists):
+    """Drop-in check with CODE OF THE REFERENCE on the other end of the socket: its `ExternalRetriever`
+    (ralm/retriever/retriever.py:68-183, imported from where it lies) connects to B200Server, sends its own encoded
+    requests -- blocking `retrieve`, the with-lists variant, and the tik-tok pattern retrieve_send / poll /
+    retrieve_recv (ralm_tiktok.py:129-192) -- and decodes our answers."""
+    import time
+    from b200ivfpq.server import B200Server
+    sys.path.insert(0, REF_RALM)
+    try:
+        from ralm.retriever.retriever import ExternalRetriever
+    finally:
+        sys.path.remove(REF_RALM)
+    index = _FakeIndex()
+    batch, k, nprobe = 4, 5, 3
+    srv = B200Server(index, port=0, batch_size=batch, dim=index.d, default_k=k, nprobe=nprobe,
+                     request_with_lists=with_lists)
+    t = threading.Thread(target=srv.start, daemon=True)
+    t.start()
+    cli = ExternalRetriever(host="127.0.0.1", port=srv.address[1], batch_size=batch, dim=index.d, default_k=k)
+    rng = np.random.default_rng(1)
+    for it in range(3):
+        q = rng.random((batch, index.d), dtype=np.float32)
+        lists = rng.integers(0, 50, size=(batch, nprobe)).astype(np.int64)
+        if with_lists:
+            D, I = index.search_preassigned(q, k, lists)
+            if it < 2:
+                ids, dists = cli.retrieve_with_lists(q, lists)
+            else:
+                cli.retrieve_with_lists_send(q, lists, k)
+                ids, dists = cli.retrieve_recv(k)
+        else:
+            D, I = index.search(q, k)
+            if it < 2:
+                ids, dists = cli.retrieve(q, k)
+            else:                                   # the asynchronous pattern the decoder loop uses
+                cli.retrieve_send(q, k)
+                deadline = time.time() + 10
+                while not cli.poll() and time.time() < deadline:
+                    time.sleep(0.001)
+                assert cli.poll(), "answer never became readable"
+                ids, dists = cli.retrieve_recv(k)
+        assert np.array_equal(np.asarray(ids, np.int64).reshape(batch, k), I)
+        assert np.array_equal(np.asarray(dists, np.float32).reshape(batch, k), D)
+    cli.socket.close()
+    t.join(timeout=5)
+    assert not t.is_alive() and srv.served == 3
+    srv.close()
