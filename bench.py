@@ -525,7 +525,9 @@ def run_ours(args):
         parity = {"queries": int(n_used),
                   "distances_bit_exact": bool(np.array_equal(Dg.view(np.uint32), Dr.view(np.uint32))),
                   "ids_identical": bool(np.array_equal(Ig, Ir)),
-                  "max_rel_dist_err": float(np.max(np.abs(Dg - Dr) / np.maximum(np.abs(Dr), 1e-30)))}
+                  "max_rel_dist_err": float(np.max(np.abs(Dg - Dr) / np.maximum(np.abs(Dr), 1e-30))),
+                  "oracle": "CPU restatement (oracle/), itself pinned against the reference's own code run as a C "
+                            "simulation (oracle/_ref: hnswlib cell selection + accelerator kernel); not the Faiss binary"}
         if gt.shape[0]:
             ng = min(gt.shape[0], n_used)
             gc = gt[:ng].cpu().numpy()
