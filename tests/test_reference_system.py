@@ -32,7 +32,7 @@ def ref(oracle):
 def _index(oracle, variant, seed, scale):
     D, M, topk, _, _ = oracle.ref_accel_dims(variant)
     rng = np.random.default_rng(seed)
-    nlist, nq = 24, 6
+    nlist, nq = 24, (6 if seed % 2 else 40)          # a latency-path batch (list segments) and a throughput-path one
     pq = (rng.standard_normal((M, 256, D // M)) * 0.3 * scale).astype(np.float32)
     cent = (rng.random((nlist, D), dtype=np.float32) * np.float32(scale)).astype(np.float32)
     xq = (rng.random((nq, D), dtype=np.float32) * np.float32(scale)).astype(np.float32)
