@@ -8,15 +8,20 @@
 Hot path = hand-written sm_100a CUDA kernels behind a C-ABI (include/b200_ivfpq.h); no CPU fallback.
 """
 from ._lib import LIB_PATH, launch_count, load as load_library
-from .compat import (GpuClonerOptions, GpuMultipleClonerOptions, GpuResourcesVector, IntVector, StandardGpuResources,
-                     cvar, deserialize_index, index_cpu_to_all_gpus, index_cpu_to_gpu, index_cpu_to_gpu_multiple,
-                     index_cpu_to_gpus_list, index_gpu_to_cpu, rev_swig_ptr, serialize_index, swig_ptr)
+from . import contrib
+from .compat import (INDICES_32_BIT, INDICES_64_BIT, INDICES_CPU, INDICES_IVF, Clustering, GpuClonerOptions,
+                     GpuMultipleClonerOptions, GpuResourcesVector, IndexIVFFlat, IntVector, PCAMatrix, StandardGpuResources,
+                     cvar, deserialize_index, float_maxheap_array_t,
+                     get_num_gpus, index_cpu_to_all_gpus, index_cpu_to_gpu, index_cpu_to_gpu_multiple,
+                     index_cpu_to_gpus_list, index_gpu_to_cpu, ranklist_intersection_size, rev_swig_ptr, serialize_index,
+                     swig_ptr, vector_float_to_array)
 from .factory import GpuParameterSpace, ParameterSpace, index_factory
 from .index import METRIC_L2, IndexFlatL2, IndexIVFPQ, InvertedLists, ProductQuantizer
-from .io import read_index, write_index
+from .io import IO_FLAG_MMAP, IO_FLAG_ONDISK_SAME_DIR, IO_FLAG_READ_ONLY, read_index, write_index
 from .retriever import AsyncB200Retriever, IndexScanner, LocalB200Retriever
 from .server import B200Client, B200Server
-from .transforms import IndexPreTransform, OPQMatrix, downcast_VectorTransform
+from .transforms import (IndexPreTransform, OPQMatrix, VectorTransform, downcast_VectorTransform, read_VectorTransform,
+                         write_VectorTransform)
 from .shards import (DistributedIndexIVFPQ, IndexReplicas, make_replica_groups, merge_shards, replica_layout, shard_index,
                      shard_index_by_list, shard_positions)
 

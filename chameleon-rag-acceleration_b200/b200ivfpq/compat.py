@@ -23,6 +23,118 @@ def rev_swig_ptr(ptr, n: int):
     return np.asarray(ptr).reshape(-1)[:int(n)]
 
 
+def get_num_gpus() -> int:
+    """faiss.get_num_gpus() (bench_gpu_performance_OSDI.py:109, faiss_retriever.py:153)."""
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def vector_float_to_array(v):
+    """faiss.vector_float_to_array(clus.centroids) (bench_gpu_1bn.py:540)."""
+    return np.asarray(v, dtype=np.float32).reshape(-1)
+
+
+def ranklist_intersection_size(k1: int, v1, k2: int, v2) -> int:
+    """faiss.ranklist_intersection_size(k1, swig_ptr(a), k2, swig_ptr(b)) (bench_gpu_1bn.py:222): how many of the first
+    k1 ids of a are among the first k2 ids of b."""
+    a = np.asarray(v1).reshape(-1)[:int(k1)]
+    b = np.asarray(v2).reshape(-1)[:int(k2)]
+    return int(np.intersect1d(a, b).shape[0])
+
+
+# GpuClonerOptions.indicesOptions values (bench_gpu_1bn.py:608); ids always live next to the codes in HBM here
+INDICES_CPU, INDICES_IVF, INDICES_32_BIT, INDICES_64_BIT = 0, 1, 2, 3
+
+
+class Clustering:
+    """faiss.Clustering(d, k) as the reference trains its coarse quantizer with it (bench_gpu_1bn.py:520-542):
+        clus = faiss.Clustering(d, k); clus.verbose = True; clus.max_points_per_centroid = 10000000
+        clus.train(x, index); centroids = faiss.vector_float_to_array(clus.centroids).reshape(k, d)
+    Lloyd iterations on the GPU (b200ivfpq.kmeans; on the CPU when no device is present); `index` receives the
+    centroids like Faiss's assignment index does."""
+
+    def __init__(self, d: int, k: int):
+        self.d, self.k = int(d), int(k)
+        self.niter, self.seed = 25, 1234
+        self.max_points_per_centroid, self.min_points_per_centroid = 256, 39
+        self.verbose = False
+        self.centroids = np.zeros(0, np.float32)
+
+    def train(self, x, index=None):
+        import torch
+        from .kmeans import kmeans
+        x = np.ascontiguousarray(x, np.float32) if not isinstance(x, torch.Tensor) else x
+        xt = torch.as_tensor(x, dtype=torch.float32)
+        if xt.dim() != 2 or xt.shape[1] != self.d:
+            raise AssertionError(f"Clustering.train: expected (n, {self.d}) vectors")
+        if torch.cuda.is_available():
+            xt = xt.cuda()
+        c = kmeans(xt, self.k, niter=self.niter, seed=self.seed, max_points_per_centroid=self.max_points_per_centroid,
+                   verbose=self.verbose)
+        self.centroids = c.reshape(-1).cpu().numpy()
+        if index is not None:
+            index.reset()
+            index.add(c if torch.cuda.is_available() else c.cpu().numpy())
+
+
+class float_maxheap_array_t:
+    """faiss.float_maxheap_array_t as the reference's ground-truth loop uses it (bench_gpu_1bn.py:427-456): nh rows of
+    the k smallest (value, id) seen so far, living IN the caller's arrays:
+        heaps.k, heaps.nh = k, nq; heaps.val = swig_ptr(D); heaps.ids = swig_ptr(I); heaps.heapify()
+        heaps.addn_with_ids(k, swig_ptr(D_block), swig_ptr(I_block), k)   # per block of the database
+        heaps.reorder()                                                   # rows ascending
+    A value replaces the current worst only if it is strictly smaller (entries already held win ties)."""
+
+    def __init__(self):
+        self.k = self.nh = 0
+        self.val = self.ids = None
+
+    def _views(self):
+        val = np.asarray(self.val).reshape(self.nh, self.k)
+        ids = np.asarray(self.ids).reshape(self.nh, self.k)
+        if not (np.shares_memory(val, self.val) and np.shares_memory(ids, self.ids)):
+            raise RuntimeError("float_maxheap_array_t: val / ids must be C-contiguous arrays (they are updated in place)")
+        return val, ids
+
+    def heapify(self):
+        val, ids = self._views()
+        val[:] = np.finfo(np.float32).max
+        ids[:] = -1
+
+    def addn_with_ids(self, nj: int, vin, id_in, id_stride: int = 0, i0: int = 0, ni: int = -1):
+        val, ids = self._views()
+        ni = self.nh - i0 if ni < 0 else ni
+        vin = np.asarray(vin, np.float32).reshape(ni, nj)
+        id_in = np.asarray(id_in, np.int64).reshape(ni, id_stride or nj)[:, :nj]
+        allv = np.concatenate([val[i0:i0 + ni], vin], axis=1)
+        alli = np.concatenate([ids[i0:i0 + ni], id_in], axis=1)
+        order = np.argsort(allv, axis=1, kind="stable")[:, :self.k]       # held entries come first among equals
+        val[i0:i0 + ni] = np.take_along_axis(allv, order, axis=1)
+        ids[i0:i0 + ni] = np.take_along_axis(alli, order, axis=1)
+
+    def reorder(self):
+        val, ids = self._views()
+        order = np.argsort(val, axis=1, kind="stable")
+        val[:] = np.take_along_axis(val, order, axis=1)
+        ids[:] = np.take_along_axis(ids, order, axis=1)
+
+
+class PCAMatrix:
+    """Named for completeness of the drivers' imports (bench_gpu_1bn.py `PCAR<d>` keys); not built: the reference's
+    hot-path configurations use OPQ or no pre-transform (BASELINE.json)."""
+
+    def __init__(self, *args, **kwargs):
+        raise RuntimeError("PCAMatrix is not supported; use OPQ<m>[_<d>] or no pre-transform")
+
+
+class IndexIVFFlat:
+    """Present so that `index.__class__ == faiss.IndexIVFFlat` tests (bench_gpu_1bn.py:692) evaluate; building one is out
+    of scope (this engine is IVF-PQ)."""
+
+    def __init__(self, *args, **kwargs):
+        raise RuntimeError("IndexIVFFlat is not supported: this engine implements IVF-PQ (IVF<nlist>,PQ<m>)")
+
+
 # ---- GPU resources / cloner options: accepted, nothing to configure ------------------------------------------------
 class StandardGpuResources:
     def setTempMemory(self, nbytes):

@@ -28,7 +28,14 @@ def write_index(index: IndexIVFPQ, fname: str) -> None:
              nbits=index.pq.nbits, nprobe=index.nprobe, is_trained=index.is_trained, **a)
 
 
-def read_index(fname: str) -> IndexIVFPQ:
+# faiss.read_index(fname, io_flags) (bench_cpu_performance.py:58,116,167): the flags choose how Faiss maps the file; the
+# lists live in HBM here, so they are accepted and have nothing to select
+IO_FLAG_MMAP = 1
+IO_FLAG_READ_ONLY = 2
+IO_FLAG_ONDISK_SAME_DIR = 4
+
+
+def read_index(fname: str, io_flags: int = 0) -> IndexIVFPQ:
     if _is_faiss_file(fname):
         z = parse_faiss_ivfpq(fname)
         index = IndexIVFPQ(IndexFlatL2(z["d"]), z["d"], z["nlist"], z["M"], z["nbits"])

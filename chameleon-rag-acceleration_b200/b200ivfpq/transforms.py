@@ -21,7 +21,18 @@ from .index import IndexIVFPQ, _as_f32_matrix, _require_cuda, _to_device
 from .kmeans import kmeans_subspaces
 
 
-class OPQMatrix:
+class VectorTransform:
+    """faiss.VectorTransform: what the drivers call a pre-processor (bench_gpu_performance_OSDI.py:230, d_in / d_out /
+    apply_py); OPQMatrix is the one the reference's factory strings produce."""
+    d_in = 0
+    d_out = 0
+    is_trained = False
+
+    def apply_py(self, x):
+        raise NotImplementedError
+
+
+class OPQMatrix(VectorTransform):
     """y = A x with A (d_out, d_in) row-major, the layout of Faiss LinearTransform.A; b = 0."""
 
     def __init__(self, d: int, M: int, d2: int = -1):
@@ -175,4 +186,22 @@ class IndexPreTransform:
 
 
 def downcast_VectorTransform(vt):
+    return vt
+
+
+def write_VectorTransform(vt: OPQMatrix, fname: str) -> None:
+    """faiss.write_VectorTransform(preproc, cachefile) (bench_gpu_1bn.py:507): the trained matrix as one .npz."""
+    if not isinstance(vt, OPQMatrix) or not vt.is_trained:
+        raise RuntimeError("write_VectorTransform: a trained OPQMatrix is required")
+    with open(fname, "wb") as f:
+        np.savez(f, kind="OPQMatrix", d_in=vt.d_in, d_out=vt.d_out, M=vt.M, A=vt.A.reshape(vt.d_out, vt.d_in))
+
+
+def read_VectorTransform(fname: str) -> OPQMatrix:
+    """faiss.read_VectorTransform(cachefile) (bench_gpu_performance_OSDI.py:520, bench_gpu_1bn.py:510)."""
+    z = np.load(fname)
+    if str(z["kind"]) != "OPQMatrix":
+        raise RuntimeError(f"read_VectorTransform: unsupported transform {z['kind']}")
+    vt = OPQMatrix(int(z["d_in"]), int(z["M"]), int(z["d_out"]))
+    vt.set_matrix(z["A"])
     return vt

@@ -232,3 +232,90 @@ def test_faiss_named_shims():
             return ("called", k, list_nos)
 
     assert search_preassigned(_Probe(), None, 7, [[1, -1]], coarse_dis=None) == ("called", 7, [[1, -1]])
+
+
+REF_ROOT = "/root/reference/Chameleon"
+# the drivers of the hot path (SURVEY.md section 8b "What calls it") and of its build / evaluation tooling (8a a10, 8f)
+REF_DRIVERS = ["llm_inference_gpu/ralm/server/faiss_server.py", "llm_inference_gpu/ralm/retriever/faiss_retriever.py",
+               "llm_inference_gpu/ralm/index_scanner/index_scanner.py", "Faiss_experiments/bench_cpu_performance.py",
+               "Faiss_experiments/bench_gpu_performance_OSDI.py", "Faiss_experiments/IVFPQ_random_dataset.py",
+               "Faiss_experiments/bench_multi_cpu_performance_OSDI.py", "Faiss_experiments/bench_gpu_1bn.py"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ROOT), reason="the reference is only mounted in the build container")
+def test_every_faiss_name_the_references_drivers_use_exists():
+    """`import b200ivfpq as faiss` must resolve every `faiss.<name>` the reference's drivers of this path mention
+    (comment lines aside): a user switching over finds the surface they call."""
+    import re
+    import b200ivfpq as faiss
+    missing = {}
+    for f in REF_DRIVERS:
+        code = "\\n".join(ln for ln in open(os.path.join(REF_ROOT, f)).read().splitlines()
+                         if not ln.strip().startswith("#"))
+        names = set(re.findall(r"\\bfaiss\\.([A-Za-z_][A-Za-z0-9_]*)", code))
+        gone = sorted(n for n in names if not hasattr(faiss, n))
+        if gone:
+            missing[f] = gone
+    assert not missing, missing
+    from b200ivfpq.contrib.ivf_tools import search_preassigned        # faiss_server.py:24, faiss_retriever.py:14
+    assert callable(search_preassigned)
+
+
+def test_ground_truth_heap_and_helpers():
+    """float_maxheap_array_t as bench_gpu_1bn.py:427-456 drives it, ranklist_intersection_size (:222), read_index's
+    second argument (bench_cpu_performance.py:116)."""
+    import inspect
+    import b200ivfpq as faiss
+    rng = np.random.default_rng(0)
+    nq, k, nb = 7, 5, 60
+    allD = rng.random((nq, nb)).astype(np.float32)
+    allD[:, 10] = allD[:, 3]                                           # an exact tie between two database entries
+    gt_I = np.zeros((nq, k), dtype="int64")
+    gt_D = np.zeros((nq, k), dtype="float32")
+    heaps = faiss.float_maxheap_array_t()
+    heaps.k, heaps.nh = k, nq
+    heaps.val, heaps.ids = faiss.swig_ptr(gt_D), faiss.swig_ptr(gt_I)
+    heaps.heapify()
+    assert (gt_I == -1).all()
+    for i0 in range(0, nb, 20):                                        # blocks of the database, as compute_GT() does
+        blk = allD[:, i0:i0 + 20]
+        I = np.argsort(blk, axis=1, kind="stable")[:, :k]
+        D = np.take_along_axis(blk, I, axis=1)
+        I = I + i0
+        heaps.addn_with_ids(k, faiss.swig_ptr(D), faiss.swig_ptr(I.astype("int64")), k)
+    heaps.reorder()
+    want = np.argsort(allD, axis=1, kind="stable")[:, :k]
+    assert np.array_equal(gt_I, want) and np.array_equal(gt_D, np.take_along_axis(allD, want, axis=1))
+    assert faiss.ranklist_intersection_size(3, faiss.swig_ptr(np.array([1, 2, 3, 4])), 3,
+                                            faiss.swig_ptr(np.array([3, 9, 1, 2]))) == 2
+    assert list(inspect.signature(faiss.read_index).parameters)[:2] == ["fname", "io_flags"] and faiss.IO_FLAG_MMAP
+    for unsupported in (faiss.IndexIVFFlat, faiss.PCAMatrix):
+        with pytest.raises(RuntimeError):
+            unsupported(None, 8, 4)
+
+
+def test_clustering_wrapper_trains_centroids():
+    """faiss.Clustering(d, k).train(x, index) as bench_gpu_1bn.py:520-542 calls it (runs on the CPU when there is no GPU)."""
+    import torch
+    import b200ivfpq as faiss
+    rng = np.random.default_rng(1)
+    centres = rng.random((8, 6)).astype(np.float32) * 10
+    x = (centres[rng.integers(0, 8, 4000)] + rng.standard_normal((4000, 6)).astype(np.float32) * 0.05).astype(np.float32)
+
+    class _Sink:
+        def reset(self):
+            self.xb = None
+
+        def add(self, c):
+            self.xb = np.asarray(c.cpu() if isinstance(c, torch.Tensor) else c)
+
+    clus = faiss.Clustering(6, 16)          # twice as many centroids as blobs: Lloyd then covers every blob
+    clus.niter = 20
+    clus.max_points_per_centroid = 10000000
+    sink = _Sink()
+    clus.train(x, sink)
+    c = faiss.vector_float_to_array(clus.centroids).reshape(16, 6)
+    assert sink.xb.shape == (16, 6) and np.allclose(sink.xb, c)
+    # every true centre has a learned centroid next to it
+    d2 = ((centres[:, None, :] - c[None, :, :]) ** 2).sum(2)
+    assert (d2.min(axis=1) < 0.05).all(), d2.min(axis=1)
