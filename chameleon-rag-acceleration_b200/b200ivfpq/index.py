@@ -89,6 +89,17 @@ class _Handle:
             pass
 
 
+class _SwigHandle:
+    """index.this.disown() / .own(): SWIG ownership calls the drivers make before handing an index to a container
+    (bench_gpu_performance_OSDI.py:624); Python owns everything here."""
+
+    def disown(self):
+        return None
+
+    def own(self):
+        return None
+
+
 class IndexFlatL2:
     """Exact L2 index (the coarse quantizer, and brute-force ground truth).
 
@@ -96,6 +107,7 @@ class IndexFlatL2:
     Reference: quantizer = faiss.IndexFlatL2(d) (IVFPQ_random_dataset.py:22); IndexScanner
     (llm_inference_gpu/ralm/index_scanner/index_scanner.py:33-73) adds centroids and searches nprobe.
     """
+    this = _SwigHandle()
 
     def __init__(self, d: int):
         self.d = int(d)
@@ -223,6 +235,7 @@ class InvertedLists:
 
 class IndexIVFPQ:
     """IVF-PQ index: faiss.IndexIVFPQ(quantizer, d, nlist, m, nbits) (IVFPQ_random_dataset.py:24)."""
+    this = _SwigHandle()
 
     def __init__(self, quantizer: IndexFlatL2, d: int, nlist: int, m: int, nbits: int = 8, metric=METRIC_L2):
         if nbits != 8:

@@ -160,17 +160,39 @@ class IndexReplicas:
     every replica (make_replica_groups); the slices are exchanged with one all-gather over it, so every rank returns
     the full (nq, k) answer like the reference's single host process does."""
 
-    def __init__(self, inner, replicas: int | None = None, replica_id: int | None = None, cross_group=None):
+    def __init__(self, inner=None, replicas: int | None = None, replica_id: int | None = None, cross_group=None):
         import torch.distributed as dist
         self.dist = dist
         self.inner = inner
         self.group = cross_group
         live = dist.is_initialized()
+        if inner is None:       # the reference's manual form: IndexReplicas() then addIndex(...) (single process)
+            replicas, replica_id = 1, 0
         self.replicas = replicas if replicas is not None else (dist.get_world_size(cross_group) if live else 1)
         self.replica_id = replica_id if replica_id is not None else (dist.get_rank(cross_group) if live else 0)
         self.d = getattr(inner, "d", None)
         self.peer_merge = getattr(inner, "peer_merge", False)
         self.peer_merge_error = getattr(inner, "peer_merge_error", None)
+        self.own_fields = False
+        self._members = [] if inner is None else [inner]
+
+    def addIndex(self, index):
+        """index = faiss.IndexReplicas(); index.addIndex(index1); index.own_fields = True
+        (bench_gpu_performance_OSDI.py:613-626).  In one process every member is a copy of the same index on the same
+        GPU, so the first one answers; across processes use the constructor arguments (one replica per rank)."""
+        if not self._members:
+            self.inner, self.d = index, getattr(index, "d", None)
+        self._members.append(index)
+
+    def count(self) -> int:
+        return len(self._members)
+
+    def at(self, i: int):
+        return self._members[i]
+
+    @property
+    def ntotal(self):
+        return getattr(self.inner, "ntotal", 0)
 
     @property
     def nprobe(self):

@@ -289,6 +289,24 @@ def test_ground_truth_heap_and_helpers():
     assert faiss.ranklist_intersection_size(3, faiss.swig_ptr(np.array([1, 2, 3, 4])), 3,
                                             faiss.swig_ptr(np.array([3, 9, 1, 2]))) == 2
     assert list(inspect.signature(faiss.read_index).parameters)[:2] == ["fname", "io_flags"] and faiss.IO_FLAG_MMAP
+    # the manual replica container of bench_gpu_performance_OSDI.py:613-626, in one process
+    class _Member:
+        d, ntotal, nprobe = 8, 123, 4
+        this = faiss.IndexFlatL2.this
+
+        def search(self, x, k):
+            return "D", "I"
+
+    rep = faiss.IndexReplicas()
+    for _ in range(2):
+        m = _Member()
+        m.this.disown()
+        rep.addIndex(m)
+    rep.own_fields = True
+    import torch
+    assert rep.count() == 2 and rep.ntotal == 123 and rep.d == 8 and rep.search(torch.zeros((3, 8)), 5) == ("D", "I")
+    faiss.ParameterSpace().set_index_parameter(rep, "nprobe", 9)
+    assert rep.at(0).nprobe == 9
     for unsupported in (faiss.IndexIVFFlat, faiss.PCAMatrix):
         with pytest.raises(RuntimeError):
             unsupported(None, 8, 4)
