@@ -188,3 +188,28 @@ def test_cuda_tie_rule_is_the_references_queue(ref, variant, k):
         index.set_lists(c["offsets"], c["codes"], c["ids"])
         return index.search_preassigned(c["xq"], kk, c["probes"])
     _check_selection_against_reference_queue(ref, variant, k, run)
+
+
+# ---- randomised shapes ------------------------------------------------------------------------------------------------
+def test_random_shapes_against_the_reference_kernels(ref):
+    """Property test (hypothesis): for random batch sizes, probe counts, cell sizes (empty cells included) and value
+    scales, the oracle's ADC distances are bit-identical to the reference HLS kernels' outputs."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(variant=st.sampled_from(VARIANTS), seed=st.integers(0, 2 ** 31 - 1), nq=st.integers(1, 3),
+           nprobe=st.integers(1, 6), max_list=st.integers(1, 70), scale=st.sampled_from([1e-3, 1.0, 255.0, 1e4]))
+    def run(variant, seed, nq, nprobe, max_list, scale):
+        c = _case(ref, variant, seed=seed, nq=nq, nprobe=nprobe, nlist=12, max_list=max_list, scale=scale)
+        lut, dist, nscan, rows = _run_reference_kernels(ref, variant, c)
+        pos = 0
+        for q in range(nq):
+            for p, l in enumerate(c["probes"][q]):
+                n = int(nscan[q, p])
+                if n:
+                    T = ref.C.lut(c["xq"][q], c["cent"][l], c["pq"])
+                    _util.assert_bit_equal(T, lut[q, p], "LUT")
+                    _util.assert_bit_equal(ref.C.adc(T, c["codes"][rows[pos:pos + n]]), dist[pos:pos + n], "ADC")
+                pos += n
+
+    run()
