@@ -2,7 +2,7 @@
 """Multi-GPU parity check, run under torchrun (one rank per GPU, NCCL):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/check_multigpu.py
+        tests/check_multigpu.py
 
 Every rank builds the same seeded index with the oracle (CPU), keeps its shard (add-order position % world),
 and searches the whole batch through DistributedIndexIVFPQ (local CUDA search -> NCCL all-gather -> K5 merge).
