@@ -337,3 +337,25 @@ def test_clustering_wrapper_trains_centroids():
     # every true centre has a learned centroid next to it
     d2 = ((centres[:, None, :] - c[None, :, :]) ** 2).sum(2)
     assert (d2.min(axis=1) < 0.05).all(), d2.min(axis=1)
+
+
+def test_vector_transform_persistence(tmp_path, monkeypatch):
+    """faiss.write_VectorTransform / read_VectorTransform (bench_gpu_1bn.py:507-510) on the OPQ matrix; the device
+    placement is patched out so that the file format round-trips without a GPU."""
+    import torch
+    import b200ivfpq as faiss
+    from b200ivfpq import transforms
+    monkeypatch.setattr(transforms, "_require_cuda", lambda: torch.device("cpu"))
+    rng = np.random.default_rng(2)
+    A = np.linalg.qr(rng.standard_normal((12, 12)))[0][:8].astype(np.float32)       # (d_out = 8, d_in = 12)
+    vt = faiss.OPQMatrix(12, 4, 8)
+    vt.set_matrix(A)
+    assert isinstance(vt, faiss.VectorTransform) and vt.is_trained and (vt.d_in, vt.d_out) == (12, 8)
+    fn = str(tmp_path / "opq.vt")
+    faiss.write_VectorTransform(vt, fn)
+    vt2 = faiss.read_VectorTransform(fn)
+    assert (vt2.d_in, vt2.d_out, vt2.M) == (12, 8, 4) and np.array_equal(vt2.A, vt.A)
+    x = rng.standard_normal((5, 12)).astype(np.float32)
+    assert np.allclose(vt2.apply_py(x), x @ A.T, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        faiss.write_VectorTransform(faiss.OPQMatrix(12, 4, 8), fn)                 # untrained
