@@ -396,6 +396,9 @@ def run_ours(args):
     D, I = step_device()
     torch.cuda.synchronize()
     stats = index.last_scan_stats()
+    fstats = index.filter_stats(reset=True) if os.environ.get("B200_IVFPQ_QL_STATS") == "1" else None
+    if fstats and rank == 0:
+        log(f"[bench] filter: {fstats} for {stats['codes']} (query, code) pairs")
     recall = None
     if rank == 0 and gt.shape[0]:
         ng = gt.shape[0]
@@ -570,7 +573,7 @@ def run_ours(args):
             "scan_ms_per_rank": [round(float(v), 3) for v in allr[:, 0]],
             "scan_gbytes_per_rank": [round(float(v) / 1e9, 2) for v in allr[:, 1]],
             "ms_per_step_per_rank": [round(float(v), 3) for v in allr[:, 2]],
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_oracle": parity,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_vs_oracle": parity, "filter_stats": fstats,
         }
         emit(line)
     if world > 1:

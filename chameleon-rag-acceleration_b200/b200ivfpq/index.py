@@ -516,6 +516,14 @@ class IndexIVFPQ:
         _lib.check(h.lib.b200_ivfpq_get_last_scan_stats(h.h, ctypes.byref(b), ctypes.byref(c)))
         return {"bytes": int(b.value), "codes": int(c.value)}
 
+    def filter_stats(self, reset: bool = True):
+        """Counters of the per-query-table filter scan since the last reset (zeros unless the handle was created with
+        B200_IVFPQ_QL_STATS=1): survivor entries, exact evaluations, work items."""
+        h = self._ensure_handle()
+        out = (ctypes.c_int64 * 3)()
+        _lib.check(h.lib.b200_ivfpq_get_filter_stats(h.h, out, 1 if reset else 0))
+        return {"survivor_entries": int(out[0]), "exact_evaluations": int(out[1]), "work_items": int(out[2])}
+
     # ------------------------------------------------------------------ flat views for the oracle / extraction
     def to_arrays(self):
         """The flat arrays the reference's extraction scripts dump: coarse (nlist, d), pq (M, 256, dsub),

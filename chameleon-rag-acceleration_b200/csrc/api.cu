@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -20,6 +21,7 @@
 #include "coarse_tc.cuh"
 #include "select_radix.cuh"
 #include "coarse_small.cuh"
+#include "qlut_api.h"
 
 using namespace b200;
 
@@ -101,11 +103,15 @@ struct b200_ivfpq_index {
     bool has_lists = false;
     int device = 0, num_sms = 148;
     int scan_variant = 0;   // 0 = auto, 1 = generic, 2 = skewed (conflict-free), 3 = two-query skewed (scan_duo.cuh),
-                            // 4 = four-query integer filter + exact survivors (scan_quad.cuh)
+                            // 4 = four-query integer filter + exact survivors (scan_quad.cuh), 5 = per-query-table filter (scan_qlut.cuh)
     int64_t max_list = 0;   // longest inverted list
     int64_t nonempty = 0;   // lists holding at least one entry (a by-list shard leaves the others empty)
     int force_nseg = 0;     // B200_IVFPQ_NSEG: override the list segmentation (tests)
     int quad_drain_at = 256;   // B200_IVFPQ_QUAD_DRAIN: survivors queued per query slot before the exact evaluation runs
+    // per-query-table filter scan (scan_qlut.cuh): per-index data (built lazily by ql_prepare) + per-batch tables
+    DevBuf ql_mu, ql_snorm, ql_sbmin, ql_sbstep, ql_lut, ql_scale, ql_amin, ql_counters;
+    float ql_pmax = 0.0f;
+    bool ql_mu_ready = false, ql_index_ready = false, ql_stats = false;
     // workspace
     DevBuf offsets, coarse_mat, probe32, hist, start, gstart, groups, order, out_keys, out_cnt, qthr, stats, pq_t, lutf, pq_maxnorm, lutg;
     DevBuf host_xq, host_D, host_I;
@@ -335,6 +341,36 @@ int launch_scan(b200_ivfpq_index* h, const ScanParams& sp, int64_t npairs, cudaS
     return 0;
 }
 
+// per-index data of the per-query-table filter scan: mu at set_codebooks time, the per-vector term when first needed
+int ql_prepare(b200_ivfpq_index* h, cudaStream_t st) {
+    int rc;
+    if (!h->ql_mu_ready) {
+        if ((rc = h->ql_mu.ensure(sizeof(float) * h->d))) return rc;
+        if (ql_build_mean(h->cent, h->nlist, h->d, h->ql_mu.as<float>(), st)) return fail(B200_IVFPQ_ECUDA, "ql_build_mean launch failed");
+        g_launches.fetch_add(1);
+        std::vector<float> mx(h->M);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(mx.data(), h->pq_maxnorm.p, sizeof(float) * h->M, cudaMemcpyDeviceToHost));
+        double a = 0.0;
+        for (float v : mx) a += (double)v * (double)v;
+        h->ql_pmax = (float)(std::sqrt(a) * 1.0001);
+        h->ql_mu_ready = true;
+        h->ql_index_ready = false;
+    }
+    if (!h->ql_index_ready) {
+        if ((rc = h->ql_snorm.ensure(sizeof(uint16_t) * std::max<int64_t>(h->ntotal, 1)))) return rc;
+        if ((rc = h->ql_sbmin.ensure(sizeof(float) * h->nlist))) return rc;
+        if ((rc = h->ql_sbstep.ensure(sizeof(float) * h->nlist))) return rc;
+        if (ql_build_index_data(h->cent, h->pq, h->ql_mu.as<float>(), h->offsets.as<int64_t>(), h->codes, h->nlist, h->d,
+                                h->M, h->dsub, h->ql_snorm.as<uint16_t>(), h->ql_sbmin.as<float>(),
+                                h->ql_sbstep.as<float>(), h->num_sms, st))
+            return fail(B200_IVFPQ_ECUDA, "ql_build_index_data launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        g_launches.fetch_add(1);
+        h->ql_index_ready = true;
+    }
+    return 0;
+}
+
 int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int nprobe, const int64_t* d_list_ids,
                 float* d_D, int64_t* d_I, cudaStream_t st) {
     if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
@@ -349,6 +385,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     CUDA_TRY(cudaSetDevice(h->device));
     if (!d_list_ids && nprobe > h->nlist) nprobe = static_cast<int>(h->nlist);   // Faiss clamps nprobe to nlist
 
+    const bool legacy = h->scan_variant == 6;   // B200_IVFPQ_SCAN=legacy: round 1's kernel selection (no scan_qlut)
+    const int sv = legacy ? 0 : h->scan_variant;
     const bool timing = h->timing;
     h->stage_valid = false;
     h->timed_chunks = 0;
@@ -372,16 +410,16 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         // as many segments as keep all work items in ONE wave of resident CTAs (two per SM); at least two below one
         // wave's worth of pairs (shorter critical path per CTA, the LUTs are prebuilt anyway)
         if (pairs < target) nseg = (int)std::max<int64_t>(2, std::min<int64_t>(16, target / pairs));
-        if (h->scan_variant >= 3) nseg = 1;   // forced multi-query kernels (tests): they scan whole lists
+        if (sv >= 3) nseg = 1;   // forced multi-query kernels (tests): they scan whole lists
         if (h->force_nseg > 0) nseg = h->force_nseg;
     }
 
     int rc;
     if ((rc = h->stats.ensure(sizeof(PairStats)))) return rc;
     if ((rc = h->probe32.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
-    if ((rc = h->hist.ensure(sizeof(int) * h->nlist))) return rc;
-    if ((rc = h->start.ensure(sizeof(int) * h->nlist))) return rc;
-    if ((rc = h->gstart.ensure(sizeof(int) * h->nlist))) return rc;
+    if ((rc = h->hist.ensure(sizeof(int) * h->nlist * kQlHostBuckets))) return rc;     // scan_qlut sorts by (rank bucket, list)
+    if ((rc = h->start.ensure(sizeof(int) * h->nlist * kQlHostBuckets))) return rc;
+    if ((rc = h->gstart.ensure(sizeof(int) * h->nlist * kQlHostBuckets))) return rc;
     if ((rc = h->groups.ensure(sizeof(QuadGroup) * qb * nprobe))) return rc;
     if ((rc = h->order.ensure(sizeof(int32_t) * qb * nprobe))) return rc;
     if ((rc = h->out_keys.ensure(sizeof(uint64_t) * qb * nprobe * k * nseg))) return rc;
@@ -412,17 +450,36 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
         int quad_ctas = 0;
         if (quad_supported(h->M, h->d, k) && aligned16 && nseg == 1 && h->max_list < (int64_t)kQuadMaxList &&
-            (h->scan_variant == 4 ||
-             (h->scan_variant == 0 && npairs >= 6 * h->nlist && h->ntotal >= kQuadMinAvgList * std::max<int64_t>(h->nonempty, 1))))
+            (sv == 4 ||
+             (sv == 0 && npairs >= 6 * h->nlist && h->ntotal >= kQuadMinAvgList * std::max<int64_t>(h->nonempty, 1))))
             quad_ctas = quad_grid(h->M, h->dsub, h->d, k, npairs, h->num_sms);
-        if (h->scan_variant == 4 && quad_ctas == 0)
+        if (sv == 4 && quad_ctas == 0)
             return fail(B200_IVFPQ_EUNSUPPORTED, "four-query scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
-        const int gsz = quad_ctas ? 4 : 2;
+        // the per-query-table filter (scan_qlut.cuh) replaces both multi-query kernels wherever lists are shared by
+        // queries: its per-work-item cost is a table copy instead of a table build
+        int ql_ctas = 0;
+        if (ql_supported_host(h->M, h->d, k) && aligned16 && nseg == 1 && h->max_list < (int64_t)kQlHostMaxList &&
+            (sv == 5 || (sv == 0 && !legacy && 2 * npairs >= h->nlist)))
+            ql_ctas = ql_grid(h->M, h->d, k, npairs, h->num_sms);
+        if (sv == 5 && ql_ctas == 0)
+            return fail(B200_IVFPQ_EUNSUPPORTED, "per-query-table scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
+        if (ql_ctas) {
+            quad_ctas = 0;
+            if ((rc = ql_prepare(h, st))) return rc;
+            if ((rc = h->ql_lut.ensure(sizeof(uint16_t) * (size_t)qb * 256 * h->M))) return rc;
+            if ((rc = h->ql_scale.ensure(sizeof(float) * qb))) return rc;
+            if ((rc = h->ql_amin.ensure(sizeof(float) * qb))) return rc;
+            if (h->ql_stats && !h->ql_counters.p) {
+                if ((rc = h->ql_counters.ensure(3 * sizeof(unsigned long long)))) return rc;
+                CUDA_TRY(cudaMemsetAsync(h->ql_counters.p, 0, 3 * sizeof(unsigned long long), st));
+            }
+        }
+        const int gsz = (quad_ctas || ql_ctas) ? 4 : 2;
         if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * quad_scratch_float4(h->M) * quad_ctas))) return rc;
 
         // pair setup
         PairStats* stats = h->stats.as<PairStats>();
-        const bool small_setup = nseg > 1 && npairs <= 8192 && npairs * nseg <= (1 << 17) && !quad_ctas;
+        const bool small_setup = nseg > 1 && npairs <= 8192 && npairs * nseg <= (1 << 17) && !quad_ctas && !ql_ctas;
         if (small_setup) {
             // latency path: one kernel instead of two memsets and four kernels; pairs keep their natural order
             pair_setup_small_kernel<<<1, 1024, 0, st>>>(probe32, (int)npairs, h->offsets.as<int64_t>(),
@@ -430,22 +487,42 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
                                                         h->out_cnt.as<int>(), (int)(npairs * nseg), stats);
             LAUNCH_CHECK();
         } else {
-            CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * h->nlist, st));
+            const int64_t nkeys = ql_ctas ? h->nlist * kQlHostBuckets : h->nlist;
+            CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * nkeys, st));
             CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs * nseg, st));
             fill_u32_kernel<<<grid1d(nqc, 256), 256, 0, st>>>(h->qthr.as<uint32_t>(), nqc, kInfBits);
             LAUNCH_CHECK();
-            pair_hist_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
-                                                                 h->hist.as<int>(), stats);
-            LAUNCH_CHECK();
-            pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), h->nlist, gsz,
+            if (ql_ctas) {
+                if (ql_launch_hist(probe32, npairs, nprobe, h->nlist, h->offsets.as<int64_t>(), h->hist.as<int>(), stats, st))
+                    return fail(B200_IVFPQ_ECUDA, "pair histogram launch failed");
+                g_launches.fetch_add(1);
+            } else {
+                pair_hist_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
+                                                                     h->hist.as<int>(), stats);
+                LAUNCH_CHECK();
+            }
+            pair_scan_kernel<<<1, 1024, 0, st>>>(h->hist.as<int>(), h->start.as<int>(), h->gstart.as<int>(), nkeys, gsz,
                                                  stats);
             LAUNCH_CHECK();
-            CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, (gsz == 4 ? sizeof(QuadGroup) : sizeof(DuoGroup)) * npairs, st));
-            pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
-                                                                    h->start.as<int>(), h->gstart.as<int>(),
-                                                                    h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p,
-                                                                    gsz);
-            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, (ql_ctas ? kQlGroupBytes : gsz == 4 ? sizeof(QuadGroup) : sizeof(DuoGroup)) * npairs, st));
+            if (ql_ctas) {
+                if (ql_launch_scatter(probe32, npairs, nprobe, h->nlist, h->offsets.as<int64_t>(), h->start.as<int>(),
+                                      h->gstart.as<int>(), h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p, st))
+                    return fail(B200_IVFPQ_ECUDA, "pair scatter launch failed");
+                g_launches.fetch_add(1);
+                // one table per QUERY (not per pair): A_q quantised with the query's own scale
+                if (ql_build_query_tables(xq, nqc, h->pq, h->ql_mu.as<float>(), h->pq_maxnorm.as<float>(), h->d, h->M,
+                                          h->dsub, h->ql_lut.as<uint16_t>(), h->ql_scale.as<float>(),
+                                          h->ql_amin.as<float>(), st))
+                    return fail(B200_IVFPQ_ECUDA, "query table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                g_launches.fetch_add(1);
+            } else {
+                pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
+                                                                        h->start.as<int>(), h->gstart.as<int>(),
+                                                                        h->hist.as<int>(), h->order.as<int32_t>(),
+                                                                        h->groups.p, gsz);
+                LAUNCH_CHECK();
+            }
         }
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));
 
@@ -474,7 +551,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         sp.lutg = nullptr;
         sp.negzero2 = 0x8000000080000000ull;
         sp.quad_drain_at = h->quad_drain_at;
-        bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && h->scan_variant != 1;
+        bool use_skew = skew_supported(h->M, h->d, k) && aligned16 && sv != 1;
         if (nseg > 1 && npairs <= 1024) {
             // small batches: every pair is scanned by nseg CTAs -- build its LUT once instead of nseg times
             if ((rc = h->lutg.ensure(sizeof(float) * npairs * h->M * 256))) return rc;
@@ -484,16 +561,29 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             LAUNCH_CHECK();
             sp.lutg = h->lutg.as<float>();
         }
-        if (h->scan_variant >= 2 && h->scan_variant != 4 && !use_skew &&
-            !(h->scan_variant == 3 && duo32_supported(h->M, h->d, k)))
+        if (sv >= 2 && sv != 4 && sv != 5 && !use_skew &&
+            !(sv == 3 && duo32_supported(h->M, h->d, k)))
             return fail(B200_IVFPQ_EUNSUPPORTED, "skewed scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
         // two queries per work item pay off once lists are shared.  With Poisson-distributed queries per list, one
         // probing query per list on average already fills 70 % of the slots (4.8 x 0.7 > the one-query kernel's
         // 2.9 TB/s); for M = 32, whose only alternative is the bank-conflicted generic kernel (2.1 TB/s), even
         // half-empty work items win (C5 sweep: profiles/r1_sweep_c5_batch_nprobe.json)
-        bool use_duo = use_skew && nseg == 1 && h->scan_variant != 2 &&
-                       (h->scan_variant == 3 || npairs >= h->nlist);
-        if (quad_ctas) {
+        bool use_duo = use_skew && nseg == 1 && sv != 2 &&
+                       (sv == 3 || npairs >= h->nlist);
+        if (ql_ctas) {
+            QlHostParams qp;
+            qp.snorm = h->ql_snorm.as<uint16_t>();
+            qp.sbmin = h->ql_sbmin.as<float>();
+            qp.sbstep = h->ql_sbstep.as<float>();
+            qp.pmax = h->ql_pmax;
+            qp.qlut = h->ql_lut.as<uint16_t>();
+            qp.qscale = h->ql_scale.as<float>();
+            qp.qamin = h->ql_amin.as<float>();
+            qp.counters = h->ql_stats ? h->ql_counters.as<unsigned long long>() : nullptr;
+            if (ql_launch_scan(sp, qp, ql_ctas, st))
+                return fail(B200_IVFPQ_ECUDA, "per-query-table scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            g_launches.fetch_add(1);
+        } else if (quad_ctas) {
             if ((rc = launch_scan_quad(sp, h->pq_t.as<float>(), quad_ctas, st)))
                 return fail(B200_IVFPQ_ECUDA, "four-query scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             g_launches.fetch_add(1);
@@ -504,8 +594,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
                 return rc;
             }
             g_launches.fetch_add(1);
-        } else if (duo32_supported(h->M, h->d, k) && aligned16 && nseg == 1 && h->scan_variant != 1 &&
-                   h->scan_variant != 2 && (h->scan_variant == 3 || 2 * npairs >= h->nlist) &&
+        } else if (duo32_supported(h->M, h->d, k) && aligned16 && nseg == 1 && sv != 1 &&
+                   sv != 2 && (sv == 3 || 2 * npairs >= h->nlist) &&
                    (rc = launch_scan_duo32(sp, h->pq_t.as<float>(), npairs, h->num_sms, st)) != -2) {
             // M = 32: two queries per work item, two alternating tables (scan_duo32.cuh)
             if (rc == -1) return fail(B200_IVFPQ_ECUDA, "two-query M=32 scan launch failed: %s",
@@ -584,13 +674,15 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
         return fail(B200_IVFPQ_ECUDA, "cannot query the current CUDA device: %s", cudaGetErrorString(e2));
     }
     const char* v = getenv("B200_IVFPQ_SCAN");
-    if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : !strcmp(v, "duo") ? 3 : !strcmp(v, "quad") ? 4 : 0;
+    if (v) h->scan_variant = !strcmp(v, "generic") ? 1 : !strcmp(v, "skew") ? 2 : !strcmp(v, "duo") ? 3 : !strcmp(v, "quad") ? 4 : !strcmp(v, "qlut") ? 5 : !strcmp(v, "legacy") ? 6 : 0;
     v = getenv("B200_IVFPQ_GRAPH");
     if (v) h->use_graph = atoi(v) != 0;
     v = getenv("B200_IVFPQ_NSEG");
     if (v) h->force_nseg = std::max(0, std::min(16, atoi(v)));
     v = getenv("B200_IVFPQ_QUAD_DRAIN");
     if (v) h->quad_drain_at = std::max(0, std::min(256, atoi(v)));
+    v = getenv("B200_IVFPQ_QL_STATS");
+    if (v) h->ql_stats = atoi(v) != 0;
     v = getenv("B200_IVFPQ_COARSE");
     if (v) h->coarse_variant = !strcmp(v, "exact") ? 1 : !strcmp(v, "matrix") ? 2 : 0;
     *out = h;
@@ -603,7 +695,8 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
     DevBuf* bufs[] = {&h->offsets, &h->coarse_mat, &h->probe32, &h->hist,   &h->start,  &h->pq_t, &h->gstart, &h->groups, &h->lutf, &h->pq_maxnorm, &h->lutg,
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
                       &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
-                      &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged, &h->cand_cnt};
+                      &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged, &h->cand_cnt,
+                      &h->ql_mu,   &h->ql_snorm,   &h->ql_sbmin, &h->ql_sbstep, &h->ql_lut, &h->ql_scale, &h->ql_amin, &h->ql_counters};
     for (DevBuf* b : bufs) b->release();
     for (auto& set : h->evs)
         for (auto& e : set)
@@ -624,6 +717,8 @@ int b200_ivfpq_set_codebooks(b200_ivfpq_t h, const float* d_centroids, const flo
     h->cent = d_centroids;
     h->pq = d_pq;
     h->state_epoch++;
+    h->ql_mu_ready = false;
+    h->ql_index_ready = false;
     {   // K1 tensor-core operands: B' = [ch | cl | ch] (nlist, kpad) bf16, ||c||^2, max ||c||^2
         CUDA_TRY(cudaSetDevice(h->device));
         h->tc_ready = false;
@@ -681,6 +776,7 @@ int b200_ivfpq_set_lists(b200_ivfpq_t h, const int64_t* h_offsets, const uint8_t
     h->nonempty = nonempty;
     h->has_lists = true;
     h->state_epoch++;
+    h->ql_index_ready = false;
     return 0;
 }
 
@@ -924,6 +1020,19 @@ int b200_ivfpq_get_stage_ms(b200_ivfpq_t h, float* h_ms5) {
             h_ms5[i] += ms;
         }
     }
+    return 0;
+}
+
+int b200_ivfpq_get_filter_stats(b200_ivfpq_t h, int64_t* h_out3, int reset) {
+    if (!h || !h_out3) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    h_out3[0] = h_out3[1] = h_out3[2] = 0;
+    if (!h->ql_counters.p) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long v[3];
+    CUDA_TRY(cudaMemcpy(v, h->ql_counters.p, sizeof(v), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 3; i++) h_out3[i] = (int64_t)v[i];
+    if (reset) CUDA_TRY(cudaMemset(h->ql_counters.p, 0, sizeof(v)));
     return 0;
 }
 

@@ -15,16 +15,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#include "topk.cuh"
+#include "scan_types.cuh"
 
 namespace b200 {
-
-constexpr int kThreads = 256;
-
-__device__ __forceinline__ float sqdiff_acc(float acc, float a, float b) {
-    float diff = __fsub_rn(a, b);
-    return __fadd_rn(acc, __fmul_rn(diff, diff));
-}
 
 // ------------------------------------------------------------------------------------------------
 // K1a: exact coarse distances.  out[q][c] = sum_j (xq[q][j] - cent[c][j])^2, j ascending.
@@ -108,14 +101,6 @@ __global__ void probes_from_i64_kernel(const int64_t* __restrict__ in, int32_t* 
 // back to back and its codes are served from L2 after the first touch.  Counting sort in three tiny
 // kernels; also accumulates the algorithmic scan statistics the roofline uses.
 // ------------------------------------------------------------------------------------------------
-struct PairStats {
-    unsigned long long scan_codes;   // sum over valid pairs of list_size
-    int nvalid;                      // number of pairs with a non-empty list
-    int work_counter;                // dynamic scheduler of scan_pairs_kernel
-    int ngroups;                     // number of same-list pair groups (scan_duo.cuh / scan_quad.cuh), sum over lists
-                                     // of ceil(cnt / group size)
-};
-
 __global__ void pair_hist_kernel(const int32_t* __restrict__ probe, int64_t npairs,
                                  const int64_t* __restrict__ offsets, int* __restrict__ hist,
                                  PairStats* __restrict__ stats) {
@@ -336,30 +321,6 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ p, int64_t n, uint32_t v)
 // widest aligned vector load M allows (VEC bytes).  A per-query global threshold (the best known k-th
 // distance over the probes finished so far) prunes candidates across the probes of a query.
 // ------------------------------------------------------------------------------------------------
-struct ScanParams {
-    const float* xq;          // (nq, d)
-    const float* cent;        // (nlist, d)
-    const float* pq;          // (M, 256, dsub)
-    const int64_t* offsets;   // (nlist + 1)
-    const uint8_t* codes;     // (ntotal, M)
-    const int32_t* probe;     // (nq * nprobe) list id or -1
-    const int32_t* order;     // (nvalid) pair indices sorted by list
-    const void* groups;       // (ngroups) work items: DuoGroup (scan_duo.cuh, scan_duo32.cuh) or QuadGroup (scan_quad.cuh)
-    float4* lutf_scratch;     // scan_quad.cuh: one fp32 LUT set (16 x 256 float4) per CTA, global memory
-    const float* pq_maxnorm;  // scan_quad.cuh: (M) max_c ||pq[m][c]||, slightly rounded up
-    uint64_t* out_keys;       // (nq * nprobe, k)
-    int* out_cnt;             // (nq * nprobe), pre-zeroed
-    uint32_t* qthr;           // (nq) per-query threshold bits, pre-set to +inf
-    PairStats* stats;
-    int d, M, dsub, nprobe, k;
-    const float* lutg;        // small batches: LUTs built once per (query, probe) pair by lut_small_kernel, or nullptr.
-                              // Layout per pair: [c][m] (M == 16, the skewed kernel's store order) or [m][c]
-    int quad_drain_at;        // scan_quad.cuh: survivors queued before the exact phase runs (<= 256)
-    uint64_t negzero2;        // (-0.0f, -0.0f): an addend ptxas cannot see through (scan_duo.cuh lut_entry_duo)
-    int nseg;                 // each (query, probe) pair is scanned by nseg CTAs (contiguous segments of its list):
-                              // fills the GPU at small batch sizes; slot = pair * nseg + segment
-};
-
 // Small batches split every (query, probe) pair into nseg list segments, one CTA each; building the pair's LUT in each
 // of those CTAs multiplies the LUT work and the PQ-codebook traffic by nseg (C4 shape: 786 KB of codebook per CTA).
 // This kernel builds every pair's LUT ONCE: grid (pair, m-chunk of 8 sub-quantizers), thread = code value.

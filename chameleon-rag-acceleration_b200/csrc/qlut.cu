@@ -1,0 +1,127 @@
+// qlut.cu -- translation unit of the per-query-table filter scan (scan_qlut.cuh): kernels + their launchers.
+#include "qlut_api.h"
+#include "scan_qlut.cuh"
+
+namespace b200 {
+
+static_assert(kQlGroupBytes == sizeof(QlGroup), "QlGroup size");
+static_assert(kQlHostMaxList == kQlMaxList, "list length limit");
+static_assert(kQlHostBuckets == kQlBuckets, "rank buckets");
+
+bool ql_supported_host(int M, int d, int k) { return ql_supported(M, d, k); }
+
+namespace {
+
+template <int M>
+int ql_grid_t(int d, int k, int64_t npairs, int num_sms) {
+    const size_t smem = ql_smem_bytes<M>(d, k);
+    if (smem > 227 * 1024) return 0;
+    auto kernel = scan_qlut_kernel<M>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QlCfg<M>::kT, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    int64_t grid = static_cast<int64_t>(per_sm) * num_sms;
+    if (grid > npairs) grid = npairs;
+    return static_cast<int>(grid < 1 ? 1 : grid);
+}
+
+template <int M>
+int ql_launch_scan_t(const ScanParams& sp, const QlParams& ql, int grid, cudaStream_t st) {
+    const size_t smem = ql_smem_bytes<M>(sp.d, sp.k);
+    auto kernel = scan_qlut_kernel<M>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    kernel<<<(unsigned)grid, QlCfg<M>::kT, smem, st>>>(sp, ql);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <int M>
+int ql_query_tables_t(const float* xq, int64_t nq, const float* pq, const float* mu, const float* pq_maxnorm, int d,
+                      int dsub, uint16_t* qlut, float* qscale, float* qamin, cudaStream_t st) {
+    constexpr int QB = 64 / M;
+    const size_t smem = sizeof(float) * QB * d;
+    auto kernel = ql_query_tables_kernel<M>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -1;
+    kernel<<<(unsigned)((nq + QB - 1) / QB), 256, smem, st>>>(xq, nq, pq, mu, pq_maxnorm, d, dsub, qlut, qscale, qamin);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace
+
+int ql_grid(int M, int d, int k, int64_t npairs, int num_sms) {
+    switch (M) {
+        case 16: return ql_grid_t<16>(d, k, npairs, num_sms);
+        case 32: return ql_grid_t<32>(d, k, npairs, num_sms);
+        case 64: return ql_grid_t<64>(d, k, npairs, num_sms);
+        default: return 0;
+    }
+}
+
+int ql_build_mean(const float* cent, int64_t nlist, int d, float* mu, cudaStream_t st) {
+    ql_mean_kernel<<<(unsigned)d, 256, 0, st>>>(cent, nlist, d, mu);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+int ql_build_index_data(const float* cent, const float* pq, const float* mu, const int64_t* offsets,
+                        const uint8_t* codes, int64_t nlist, int d, int M, int dsub, uint16_t* snorm, float* sbmin,
+                        float* sbstep, int num_sms, cudaStream_t st) {
+    const size_t smem = sizeof(double) * M * 256;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(ql_sb_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -1;
+    int64_t grid = std::min<int64_t>(nlist, 8ll * num_sms);
+    ql_sb_build_kernel<<<(unsigned)grid, 256, smem, st>>>(cent, pq, mu, offsets, codes, nlist, d, M, dsub, snorm, sbmin,
+                                                          sbstep);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+int ql_build_query_tables(const float* xq, int64_t nq, const float* pq, const float* mu, const float* pq_maxnorm, int d,
+                          int M, int dsub, uint16_t* qlut, float* qscale, float* qamin, cudaStream_t st) {
+    switch (M) {
+        case 16: return ql_query_tables_t<16>(xq, nq, pq, mu, pq_maxnorm, d, dsub, qlut, qscale, qamin, st);
+        case 32: return ql_query_tables_t<32>(xq, nq, pq, mu, pq_maxnorm, d, dsub, qlut, qscale, qamin, st);
+        case 64: return ql_query_tables_t<64>(xq, nq, pq, mu, pq_maxnorm, d, dsub, qlut, qscale, qamin, st);
+        default: return -1;
+    }
+}
+
+int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets, int* hist,
+                   PairStats* stats, cudaStream_t st) {
+    ql_pair_hist_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, nprobe, nlist, offsets, hist, stats);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets,
+                      const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, cudaStream_t st) {
+    ql_pair_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, nprobe, nlist, offsets, start,
+                                                                           gstart, cursor, order,
+                                                                           static_cast<QlGroup*>(groups));
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+int ql_launch_scan(const ScanParams& sp, const QlHostParams& qp, int grid, cudaStream_t st) {
+    QlParams ql;
+    ql.snorm = qp.snorm;
+    ql.sbmin = qp.sbmin;
+    ql.sbstep = qp.sbstep;
+    ql.pmax = qp.pmax;
+    ql.qlut = qp.qlut;
+    ql.qscale = qp.qscale;
+    ql.qamin = qp.qamin;
+    ql.counters = qp.counters;
+    switch (sp.M) {
+        case 16: return ql_launch_scan_t<16>(sp, ql, grid, st);
+        case 32: return ql_launch_scan_t<32>(sp, ql, grid, st);
+        case 64: return ql_launch_scan_t<64>(sp, ql, grid, st);
+        default: return -1;
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,49 @@
+// qlut_api.h -- host entry points of the per-query-table filter scan (scan_qlut.cuh), compiled in qlut.cu.
+// All pointers are device pointers unless named h_*; every function returns 0, or -1 after a CUDA error (the caller
+// reads cudaGetLastError / cudaPeekAtLastError).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "scan_types.cuh"
+
+namespace b200 {
+
+struct QlHostParams {
+    // per index (built by ql_build_index_data)
+    const uint16_t* snorm;
+    const float* sbmin;
+    const float* sbstep;
+    float pmax;
+    // per batch (built by ql_build_query_tables)
+    const uint16_t* qlut;
+    const float* qscale;
+    const float* qamin;
+    unsigned long long* counters;   // 3 counters or nullptr
+};
+
+constexpr uint32_t kQlHostMaxList = 1u << 28;
+constexpr size_t kQlGroupBytes = 32;
+
+bool ql_supported_host(int M, int d, int k);
+// CTAs to launch (resident CTAs per SM x SMs, capped by the number of pairs); 0 when the kernel does not fit
+int ql_grid(int M, int d, int k, int64_t npairs, int num_sms);
+// mu (d floats) = mean of the coarse centroids
+int ql_build_mean(const float* cent, int64_t nlist, int d, float* mu, cudaStream_t st);
+// snorm (ntotal u16), sbmin / sbstep (nlist f32) from the codes
+int ql_build_index_data(const float* cent, const float* pq, const float* mu, const int64_t* offsets,
+                        const uint8_t* codes, int64_t nlist, int d, int M, int dsub, uint16_t* snorm, float* sbmin,
+                        float* sbstep, int num_sms, cudaStream_t st);
+// qlut (nq, 256, M) u16, qscale / qamin (nq) f32
+int ql_build_query_tables(const float* xq, int64_t nq, const float* pq, const float* mu, const float* pq_maxnorm, int d,
+                          int M, int dsub, uint16_t* qlut, float* qscale, float* qamin, cudaStream_t st);
+// pair setup with the key (rank bucket, list): hist / start / gstart / cursor hold kQlHostBuckets * nlist entries
+constexpr int kQlHostBuckets = 3;
+int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets, int* hist,
+                   PairStats* stats, cudaStream_t st);
+int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets,
+                      const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, cudaStream_t st);
+int ql_launch_scan(const ScanParams& sp, const QlHostParams& qp, int grid, cudaStream_t st);
+
+}  // namespace b200

@@ -132,6 +132,11 @@ B200_API int b200_ivfpq_get_stage_ms(b200_ivfpq_t h, float* h_ms5);
  * synchronises the stream of that search. */
 B200_API int b200_ivfpq_get_last_scan_stats(b200_ivfpq_t h, int64_t* h_bytes, int64_t* h_codes);
 
+/* instrumentation of the per-query-table filter scan (csrc/scan_qlut.cuh), accumulated over the searches since the
+ * last reset when the handle was created with B200_IVFPQ_QL_STATS=1: [0] survivor entries queued by the integer
+ * filter, [1] exact fp32 evaluations, [2] work items.  All zero when the statistics are off.  Synchronises. */
+B200_API int b200_ivfpq_get_filter_stats(b200_ivfpq_t h, int64_t* h_out3, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,174 @@
+"""Parity of the per-query-table filter scan (csrc/scan_qlut.cuh) with the oracle.
+
+The kernel filters codes with an integer lower bound built from a per-QUERY table and a per-VECTOR 16-bit term, and
+evaluates the survivors exactly from the codebook.  It must return exactly the oracle's results -- distances bit for
+bit, ids, ties in scan order -- whatever the data looks like: the cases below include SIFT-scale values, data far from
+the origin (where the decomposition cancels badly), the reference's own toy generator with its 0..n/1000 ramp on
+dimension 0 (IVFPQ_random_dataset.py:6-13), duplicate codes, empty lists, k = 1 .. 500 and M = 16 / 32 / 64.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import _util
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(a, variant="qlut", stats=False):
+    import b200ivfpq as faiss
+    old = {k: os.environ.get(k) for k in ("B200_IVFPQ_SCAN", "B200_IVFPQ_QL_STATS")}
+    os.environ["B200_IVFPQ_SCAN"] = variant
+    if stats:
+        os.environ["B200_IVFPQ_QL_STATS"] = "1"
+    try:
+        index = faiss.IndexIVFPQ(faiss.IndexFlatL2(a["d"]), a["d"], a["nlist"], a["M"], 8)
+        index.set_codebooks(a["coarse"], a["pq"])
+        index.set_lists(a["offsets"], a["codes"], a["ids"])
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return index
+
+
+def _check(oracle, a, xq, nprobe, k, what, repeats=2):
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+    index = _load(a)
+    index.nprobe = nprobe
+    for _ in range(repeats):      # the grouping of queries depends on atomics' order; the results must not
+        D, I = index.search(xq, k)
+        _util.assert_bit_equal(D, Dr, f"D ({what})")
+        _util.assert_bit_equal(I, Ir, f"I ({what})")
+    return index
+
+
+@pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used,M", [
+    (128, 24, 60000, 103, 5, 10, None, 16),     # group sizes 1..4, several tiles per list
+    (96, 16, 12000, 64, 16, 100, 13, 16),       # dsub 6, k = 100, empty lists, every query probes every list
+    (64, 8, 3000, 1, 8, 10, None, 16),          # one query: every group is a single
+    (256, 12, 5000, 37, 3, 7, None, 16),        # dsub 16
+    (80, 12, 5000, 40, 4, 10, None, 16),        # dsub 5
+    (128, 4, 9000, 200, 4, 1, None, 16),        # k = 1, 200 queries on every list
+    (128, 24, 60000, 103, 5, 10, None, 32),     # M = 32 (C5 shape, dsub 4): two chunk tables, 10-bit entries
+    (256, 16, 12000, 64, 16, 100, 13, 32),      # M = 32, dsub 8, k = 100, empty lists
+    (192, 6, 2500, 9, 6, 10, None, 32),         # M = 32, dsub 6
+    (768, 12, 9000, 40, 4, 10, None, 64),       # M = 64 (C4 / RALM shape, dsub 12): four chunk tables, 9-bit entries
+    (128, 6, 2000, 9, 6, 20, 5, 64),            # M = 64, dsub 2, an empty list
+    (128, 10, 30000, 64, 10, 500, None, 16),    # k = 500: shared-memory bitonic folds
+])
+def test_qlut_scan_bit_exact(oracle, d, nlist, n, nq, nprobe, k, used, M):
+    a = _util.make_index_arrays(oracle, 190 + d + M, d, nlist, M, n, used_lists=used)
+    if d == 128 and nlist == 4:
+        rng = np.random.default_rng(5)
+        a["codes"] = np.ascontiguousarray(a["codes"][rng.integers(0, 500, size=a["codes"].shape[0])])   # heavy ties
+    xq = _util.make_queries(17, a, nq)
+    _check(oracle, a, xq, nprobe, k, f"qlut M={M}")
+
+
+def _scaled(oracle, seed, d, nlist, M, n, nq, scale, shift):
+    """Clustered data times `scale` plus `shift` on every coordinate; codebooks trained by a few Lloyd steps so that the
+    codes are meaningful at that scale."""
+    rng = np.random.default_rng(seed)
+    dsub = d // M
+    cent0 = rng.random((nlist, d), dtype=np.float32)
+    x = cent0[rng.integers(0, nlist, n)] + 0.08 * rng.standard_normal((n, d)).astype(np.float32)
+    x = (x * scale + shift).astype(np.float32)
+    coarse = (cent0 * scale + shift).astype(np.float32)
+    list_no = oracle.C.assign(x, coarse)
+    res = x - coarse[list_no]
+    pq = np.stack([res[rng.integers(0, n, 256), m * dsub:(m + 1) * dsub] for m in range(M)]).astype(np.float32)
+    codes = oracle.C.encode(x, coarse, list_no, pq)
+    order = np.argsort(list_no, kind="stable")
+    offsets = np.zeros(nlist + 1, np.int64)
+    offsets[1:] = np.cumsum(np.bincount(list_no, minlength=nlist))
+    a = {"coarse": coarse, "pq": np.ascontiguousarray(pq), "offsets": offsets, "codes": np.ascontiguousarray(codes[order]),
+         "ids": np.arange(n, dtype=np.int64)[order].copy(), "d": d, "nlist": nlist, "M": M}
+    xq = (cent0[rng.integers(0, nlist, nq)] + 0.08 * rng.standard_normal((nq, d)).astype(np.float32))
+    return a, (xq * scale + shift).astype(np.float32)
+
+
+@pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (255.0, 0.0), (1.0, 1000.0), (1e-3, 0.0), (1.0, -37.5), (3e4, 1e6)])
+def test_qlut_scan_at_any_scale(oracle, scale, shift):
+    """Magnitudes and offsets only change how much the filter removes, never the result."""
+    a, xq = _scaled(oracle, 77, 128, 20, 16, 40000, 96, scale, shift)
+    _check(oracle, a, xq, 6, 10, f"scale {scale} shift {shift}")
+
+
+def test_qlut_scan_reference_toy_generator(oracle):
+    """IVFPQ_random_dataset.py:6-13: uniform data with x[:, 0] += arange(n) / 1000."""
+    rng = np.random.default_rng(1234)
+    n, d, nlist, M, nq = 50000, 64, 16, 16, 50
+    x = rng.random((n, d)).astype(np.float32)
+    x[:, 0] += np.arange(n) / 1000.0
+    xq = rng.random((nq, d)).astype(np.float32)
+    xq[:, 0] += np.arange(nq) / 1000.0
+    coarse = x[rng.choice(n, nlist, replace=False)].copy()
+    list_no = oracle.C.assign(x, coarse)
+    res = x - coarse[list_no]
+    dsub = d // M
+    pq = np.stack([res[rng.integers(0, n, 256), m * dsub:(m + 1) * dsub] for m in range(M)]).astype(np.float32)
+    codes = oracle.C.encode(x, coarse, list_no, pq)
+    order = np.argsort(list_no, kind="stable")
+    offsets = np.zeros(nlist + 1, np.int64)
+    offsets[1:] = np.cumsum(np.bincount(list_no, minlength=nlist))
+    a = {"coarse": coarse, "pq": np.ascontiguousarray(pq), "offsets": offsets, "codes": np.ascontiguousarray(codes[order]),
+         "ids": np.arange(n, dtype=np.int64)[order].copy(), "d": d, "nlist": nlist, "M": M}
+    _check(oracle, a, xq, 8, 10, "toy generator")
+
+
+def test_qlut_ties_follow_scan_order(oracle):
+    rng = np.random.default_rng(3)
+    a = _util.make_index_arrays(oracle, 6, 64, 8, 16, 4000)
+    a["codes"] = np.ascontiguousarray(a["codes"][rng.integers(0, 40, size=a["codes"].shape[0])])   # 40 distinct codes
+    xq = _util.make_queries(2, a, 30)
+    Dr, _ = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 8, 50)
+    assert any(len(set(_util.bits(r).tolist())) < 50 for r in Dr), "test needs real ties"
+    _check(oracle, a, xq, 8, 50, "ties")
+
+
+def test_qlut_degenerate_inputs(oracle):
+    """A zero PQ codebook (every table entry equal: scale 0), queries equal to a centroid, and a query of zeros."""
+    a = _util.make_index_arrays(oracle, 9, 64, 6, 16, 3000)
+    xq = _util.make_queries(4, a, 12)
+    xq[0] = a["coarse"][2]
+    xq[1] = 0.0
+    _check(oracle, a, xq, 6, 10, "centroid / zero query")
+    a["pq"] = np.zeros_like(a["pq"])
+    _check(oracle, a, xq, 6, 10, "zero codebook")
+
+
+def test_qlut_filter_actually_filters(oracle):
+    """The exact path alone would also pass the parity tests: make sure the filter does the work."""
+    import b200ivfpq as faiss
+    a, xq = _scaled(oracle, 5, 128, 16, 16, 120000, 256, 1.0, 0.0)
+    index = _load(a, stats=True)
+    index.nprobe = 8
+    D, I = index.search(xq, 10)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 8, 10)
+    _util.assert_bit_equal(D, Dr, "D")
+    _util.assert_bit_equal(I, Ir, "I")
+    out = (ctypes.c_int64 * 3)()
+    h = index._ensure_handle()
+    faiss._lib.check(h.lib.b200_ivfpq_get_filter_stats(h.h, out, 1))
+    codes = index.last_scan_stats()["codes"]
+    assert out[2] > 0 and out[1] > 0
+    assert out[1] < 0.1 * codes, f"{out[1]} exact evaluations for {codes} (query, code) pairs: the filter is not filtering"
+
+
+def test_qlut_lists_replaced(oracle):
+    """set_lists again (index.add after a search): the per-vector term is rebuilt."""
+    a = _util.make_index_arrays(oracle, 21, 64, 8, 16, 6000)
+    xq = _util.make_queries(5, a, 40)
+    index = _check(oracle, a, xq, 4, 10, "first lists")
+    b = _util.make_index_arrays(oracle, 22, 64, 8, 16, 9000)
+    index.set_codebooks(b["coarse"], b["pq"])
+    index.set_lists(b["offsets"], b["codes"], b["ids"])
+    Dr, Ir = oracle.C.search(xq, b["coarse"], b["pq"], b["offsets"], b["codes"], b["ids"], 4, 10)
+    D, I = index.search(xq, 10)
+    _util.assert_bit_equal(D, Dr, "D (second lists)")
+    _util.assert_bit_equal(I, Ir, "I (second lists)")
