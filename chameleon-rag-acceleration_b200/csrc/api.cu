@@ -110,6 +110,12 @@ struct b200_ivfpq_index {
     int quad_drain_at = 256;   // B200_IVFPQ_QUAD_DRAIN: survivors queued per query slot before the exact evaluation runs
     // per-query-table filter scan (scan_qlut.cuh): per-index data (built lazily by ql_prepare) + per-batch tables
     DevBuf ql_mu, ql_snorm, ql_sbmin, ql_sbstep, ql_lut, ql_scale, ql_amin, ql_counters;
+    // streaming pipeline (scan_stream.cuh)
+    DevBuf st_srec, st_sfill, st_ctr, st_slab, st_qcnt, st_qflag, st_qkey, st_prefix, st_pdis;
+    int st_mode = 1;            // B200_IVFPQ_STREAM=0: in-kernel top-k (scan_qlut_kernel) instead of the streaming pipeline
+    double st_rate = 0.01;      // B200_IVFPQ_STREAM_RATE: survivor records provisioned per (query, code) pair
+    int st_capq = 0;            // B200_IVFPQ_STREAM_CAPQ: keys per query slab (0 = max(1024, 32 k))
+    double st_minrec = 4.0 * 1048576.0;   // B200_IVFPQ_STREAM_MINREC: lower bound of the record buffer (tests shrink it)
     float ql_pmax = 0.0f;
     bool ql_mu_ready = false, ql_index_ready = false, ql_stats = false;
     // workspace
@@ -463,6 +469,35 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             ql_ctas = ql_grid(h->M, h->d, k, npairs, h->num_sms);
         if (sv == 5 && ql_ctas == 0)
             return fail(B200_IVFPQ_EUNSUPPORTED, "per-query-table scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
+        int st_ctas = 0;
+        StHostBuffers sb{};
+        if (ql_ctas && h->st_mode) st_ctas = st_filter_grid(h->M, npairs, h->num_sms);
+        if (st_ctas) {
+            // survivor records: a share of the (query, code) pairs the batch scans; slabs: keys at or below a
+            // query's bootstrap threshold.  An overflow is detected on the device and answered by the fallback launches.
+            const double visits = (double)npairs * (double)h->ntotal / (double)std::max<int64_t>(h->nonempty, 1);
+            const double want = std::min(std::max(visits * h->st_rate, h->st_minrec), 192.0 * 1048576.0);
+            sb.max_chunks = (unsigned int)(want / kStChunkRecords);
+            sb.capq = h->st_capq > 0 ? h->st_capq : std::max(2048, 32 * k);
+            if ((rc = h->st_srec.ensure((size_t)sb.max_chunks * kStChunkRecords * 8))) return rc;
+            if ((rc = h->st_sfill.ensure((size_t)sb.max_chunks * 4))) return rc;
+            if ((rc = h->st_ctr.ensure(kStCtrBytes))) return rc;
+            if ((rc = h->st_slab.ensure((size_t)qb * sb.capq * 8))) return rc;
+            if ((rc = h->st_qcnt.ensure((size_t)qb * 4))) return rc;
+            if ((rc = h->st_qflag.ensure((size_t)qb * 4))) return rc;
+            if ((rc = h->st_qkey.ensure((size_t)qb * 8))) return rc;
+            if ((rc = h->st_prefix.ensure((size_t)qb * nprobe * 4))) return rc;
+            if ((rc = h->st_pdis.ensure((size_t)qb * nprobe * 4))) return rc;
+            sb.srec = h->st_srec.p;
+            sb.sfill = h->st_sfill.p;
+            sb.ctr = h->st_ctr.p;
+            sb.slab = h->st_slab.p;
+            sb.qcnt = h->st_qcnt.p;
+            sb.qflag = h->st_qflag.p;
+            sb.qkey = h->st_qkey.p;
+            sb.prefix = h->st_prefix.p;
+            sb.pdis = h->st_pdis.p;
+        }
         if (ql_ctas) {
             quad_ctas = 0;
             if ((rc = ql_prepare(h, st))) return rc;
@@ -527,6 +562,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));
 
         // K2+K3+K4
+        const int* stream_guard = nullptr;   // set when the streaming pipeline ran: what follows is its fallback
+        const int* stream_qflag = nullptr;
         ScanParams sp;
         sp.xq = xq;
         sp.cent = h->cent;
@@ -580,9 +617,22 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             qp.qscale = h->ql_scale.as<float>();
             qp.qamin = h->ql_amin.as<float>();
             qp.counters = h->ql_stats ? h->ql_counters.as<unsigned long long>() : nullptr;
+            qp.guard = nullptr;
+            qp.qflag = nullptr;
+            if (st_ctas) {
+                // streaming pipeline: thresholds -> filter -> exact evaluation -> select; D / I are final after it ...
+                if (st_launch(sp, qp, sb, nqc, h->ids, d_D + q0 * k, d_I + q0 * k, st_ctas, h->num_sms, st))
+                    return fail(B200_IVFPQ_ECUDA, "streaming scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                g_launches.fetch_add(4);
+                // ... unless a buffer overflowed: then the guarded launches below recompute the batch
+                qp.guard = st_overflow_flag(sb.ctr);
+                qp.qflag = h->st_qflag.as<int>();
+            }
             if (ql_launch_scan(sp, qp, ql_ctas, st))
                 return fail(B200_IVFPQ_ECUDA, "per-query-table scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             g_launches.fetch_add(1);
+            stream_guard = qp.guard;
+            stream_qflag = qp.qflag;
         } else if (quad_ctas) {
             if ((rc = launch_scan_quad(sp, h->pq_t.as<float>(), quad_ctas, st)))
                 return fail(B200_IVFPQ_ECUDA, "four-query scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -624,7 +674,8 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if ((rc = set_smem(merge_query_kernel, msmem))) return rc;
         merge_query_kernel<<<(unsigned)nqc, kThreads, msmem, st>>>(h->out_keys.as<uint64_t>(), h->out_cnt.as<int>(),
                                                                   probe32, h->offsets.as<int64_t>(), h->ids, nprobe, k,
-                                                                  nseg, h->qthr.as<uint32_t>(), d_D + q0 * k, d_I + q0 * k);
+                                                                  nseg, h->qthr.as<uint32_t>(), d_D + q0 * k, d_I + q0 * k,
+                                                                  stream_guard, stream_qflag);
         LAUNCH_CHECK();
         if (tm) {
             CUDA_TRY(cudaEventRecord(h->ev[5], st));
@@ -681,6 +732,14 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     if (v) h->force_nseg = std::max(0, std::min(16, atoi(v)));
     v = getenv("B200_IVFPQ_QUAD_DRAIN");
     if (v) h->quad_drain_at = std::max(0, std::min(256, atoi(v)));
+    v = getenv("B200_IVFPQ_STREAM");
+    if (v) h->st_mode = atoi(v);
+    v = getenv("B200_IVFPQ_STREAM_CAPQ");
+    if (v) h->st_capq = std::max(16, atoi(v));
+    v = getenv("B200_IVFPQ_STREAM_MINREC");
+    if (v) h->st_minrec = std::max(64.0, atof(v));
+    v = getenv("B200_IVFPQ_STREAM_RATE");
+    if (v) h->st_rate = std::max(1e-6, atof(v));
     v = getenv("B200_IVFPQ_QL_STATS");
     if (v) h->ql_stats = atoi(v) != 0;
     v = getenv("B200_IVFPQ_COARSE");
@@ -696,7 +755,8 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
                       &h->order,   &h->out_keys,   &h->out_cnt, &h->qthr,   &h->stats,  &h->host_xq,
                       &h->host_D,  &h->host_I,     &h->cent_bf16, &h->cnorm, &h->cmax2,
                       &h->q_bf16,  &h->qnorm,      &h->cand,   &h->cand_score, &h->flags, &h->nflagged, &h->cand_cnt,
-                      &h->ql_mu,   &h->ql_snorm,   &h->ql_sbmin, &h->ql_sbstep, &h->ql_lut, &h->ql_scale, &h->ql_amin, &h->ql_counters};
+                      &h->ql_mu,   &h->ql_snorm,   &h->ql_sbmin, &h->ql_sbstep, &h->ql_lut, &h->ql_scale, &h->ql_amin, &h->ql_counters,
+                      &h->st_srec, &h->st_sfill, &h->st_ctr, &h->st_slab, &h->st_qcnt, &h->st_qflag, &h->st_qkey, &h->st_prefix, &h->st_pdis};
     for (DevBuf* b : bufs) b->release();
     for (auto& set : h->evs)
         for (auto& e : set)
@@ -1026,12 +1086,39 @@ int b200_ivfpq_get_stage_ms(b200_ivfpq_t h, float* h_ms5) {
 int b200_ivfpq_get_filter_stats(b200_ivfpq_t h, int64_t* h_out3, int reset) {
     if (!h || !h_out3) return fail(B200_IVFPQ_EINVAL, "null pointer");
     h_out3[0] = h_out3[1] = h_out3[2] = 0;
-    if (!h->ql_counters.p) return 0;
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
+    if (h->st_ctr.p) {   // streaming pipeline: counters of the LAST chunk of the last search
+        unsigned char raw[kStCtrBytes];
+        CUDA_TRY(cudaMemcpy(raw, h->st_ctr.p, kStCtrBytes, cudaMemcpyDeviceToHost));
+        unsigned int nchunks;
+        int ovf;
+        unsigned long long rec, ev;
+        memcpy(&nchunks, raw, 4);
+        memcpy(&ovf, raw + 4, 4);
+        memcpy(&rec, raw + 8, 8);
+        memcpy(&ev, raw + 16, 8);
+        h_out3[0] = (int64_t)rec;
+        h_out3[1] = (int64_t)ev;
+        if (getenv("B200_IVFPQ_STREAM_DEBUG")) {
+            unsigned long long kept;
+            unsigned int mx, nf;
+            memcpy(&kept, raw + 24, 8);
+            memcpy(&mx, raw + 32, 4);
+            memcpy(&nf, raw + 36, 4);
+            fprintf(stderr, "[stream] chunks %u overflow %d records %llu evals %llu kept %llu max slab %u flagged queries %u\n",
+                    nchunks, ovf, rec, ev, kept, mx, nf);
+        }
+        h_out3[2] = ovf ? -(int64_t)ovf : (int64_t)nchunks;
+    }
+    if (!h->ql_counters.p) return 0;
     unsigned long long v[3];
     CUDA_TRY(cudaMemcpy(v, h->ql_counters.p, sizeof(v), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 3; i++) h_out3[i] = (int64_t)v[i];
+    if (!h->st_ctr.p) {
+        for (int i = 0; i < 3; i++) h_out3[i] = (int64_t)v[i];
+    } else if (h_out3[2] < 0) {   // the fallback launches ran: their work counts too
+        for (int i = 0; i < 2; i++) h_out3[i] += (int64_t)v[i];
+    }
     if (reset) CUDA_TRY(cudaMemset(h->ql_counters.p, 0, sizeof(v)));
     return 0;
 }

@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(int* __restrict__ hist,
         stats->nvalid = carry;
         stats->ngroups = gcarry;
         stats->work_counter = 0;
+        stats->work_counter2 = 0;
     }
 }
 
@@ -515,7 +516,14 @@ __global__ void __launch_bounds__(kThreads) merge_query_kernel(const uint64_t* _
                                                                const int64_t* __restrict__ offsets,
                                                                const int64_t* __restrict__ ids, int nprobe, int k,
                                                                int nseg, const uint32_t* __restrict__ qthr,
-                                                               float* __restrict__ D, int64_t* __restrict__ I) {
+                                                               float* __restrict__ D, int64_t* __restrict__ I,
+                                                               const int* __restrict__ guard,
+                                                               const int* __restrict__ qflag) {
+    // guard: a fallback launch (scan_stream.cuh): all queries if (*guard & 3), else only the queries with qflag[q] != 0
+    if (guard) {
+        const int ov = *reinterpret_cast<const volatile int*>(guard);
+        if (ov == 0 || ((ov & 3) == 0 && qflag[blockIdx.x] == 0)) return;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TopK tk;
     tk.bind(smem_raw, k, kMergeCap);

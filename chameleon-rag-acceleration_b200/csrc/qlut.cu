@@ -1,6 +1,7 @@
 // qlut.cu -- translation unit of the per-query-table filter scan (scan_qlut.cuh): kernels + their launchers.
 #include "qlut_api.h"
 #include "scan_qlut.cuh"
+#include "scan_stream.cuh"
 
 namespace b200 {
 
@@ -116,10 +117,110 @@ int ql_launch_scan(const ScanParams& sp, const QlHostParams& qp, int grid, cudaS
     ql.qscale = qp.qscale;
     ql.qamin = qp.qamin;
     ql.counters = qp.counters;
+    ql.guard = qp.guard;
+    ql.qflag = qp.qflag;
     switch (sp.M) {
         case 16: return ql_launch_scan_t<16>(sp, ql, grid, st);
         case 32: return ql_launch_scan_t<32>(sp, ql, grid, st);
         case 64: return ql_launch_scan_t<64>(sp, ql, grid, st);
+        default: return -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static_assert(sizeof(StCounters) <= kStCtrBytes, "StCounters size");
+static_assert(kStChunkRecords == kStChunk, "chunk size");
+
+const int* st_overflow_flag(const void* ctr) { return &static_cast<const StCounters*>(ctr)->overflow; }
+
+namespace {
+
+template <int M>
+int st_filter_grid_t(int64_t npairs, int num_sms) {
+    const size_t smem = st_filter_smem<M>();
+    auto kernel = st_filter_kernel<M>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, QlCfg<M>::kT, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    int64_t grid = static_cast<int64_t>(per_sm) * num_sms;
+    if (grid > npairs) grid = npairs;
+    return static_cast<int>(grid < 1 ? 1 : grid);
+}
+
+template <int M>
+int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
+                cudaStream_t st) {
+    const size_t bsm = st_boot_smem(sp.d, M, sp.nprobe, sp.k);
+    if (bsm > 48 * 1024 &&
+        cudaFuncSetAttribute(st_boot_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm) != cudaSuccess)
+        return -1;
+    st_boot_kernel<M><<<(unsigned)nq, kStBootThreads, bsm, st>>>(sp.xq, sp.cent, sp.pq, sp.offsets, sp.codes, sp.probe,
+                                                                 sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr);
+    if (cudaPeekAtLastError() != cudaSuccess) return -1;
+    const size_t fsm = st_filter_smem<M>();
+    if (cudaFuncSetAttribute(st_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
+    st_filter_kernel<M><<<(unsigned)filter_grid, QlCfg<M>::kT, fsm, st>>>(sp, ql, stp);
+    if (cudaPeekAtLastError() != cudaSuccess) return -1;
+    st_eval_kernel<M><<<(unsigned)(8 * num_sms), 256, 0, st>>>(sp, stp);
+    if (cudaPeekAtLastError() != cudaSuccess) return -1;
+    const size_t ssm = TopK::smem_bytes(sp.k, kStSelCap);
+    if (ssm > 48 * 1024 &&
+        cudaFuncSetAttribute(st_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm) != cudaSuccess)
+        return -1;
+    st_select_kernel<<<(unsigned)nq, kThreads, ssm, st>>>(stp, sp.probe, sp.offsets, sp.nprobe, sp.k);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace
+
+int st_filter_grid(int M, int64_t npairs, int num_sms) {
+    switch (M) {
+        case 16: return st_filter_grid_t<16>(npairs, num_sms);
+        case 32: return st_filter_grid_t<32>(npairs, num_sms);
+        case 64: return st_filter_grid_t<64>(npairs, num_sms);
+        default: return 0;
+    }
+}
+
+int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,
+              int64_t* I, int filter_grid, int num_sms, cudaStream_t st) {
+    QlParams ql;
+    ql.snorm = qp.snorm;
+    ql.sbmin = qp.sbmin;
+    ql.sbstep = qp.sbstep;
+    ql.pmax = qp.pmax;
+    ql.qlut = qp.qlut;
+    ql.qscale = qp.qscale;
+    ql.qamin = qp.qamin;
+    ql.counters = nullptr;
+    ql.guard = nullptr;
+    ql.qflag = nullptr;
+    StParams stp;
+    stp.srec = static_cast<uint2*>(sb.srec);
+    stp.sfill = static_cast<unsigned int*>(sb.sfill);
+    stp.max_chunks = sb.max_chunks;
+    stp.ctr = static_cast<StCounters*>(sb.ctr);
+    stp.slab = static_cast<uint64_t*>(sb.slab);
+    stp.qcnt = static_cast<unsigned int*>(sb.qcnt);
+    stp.qflag = static_cast<int*>(sb.qflag);
+    stp.qkey = static_cast<uint64_t*>(sb.qkey);
+    stp.capq = sb.capq;
+    stp.prefix = static_cast<uint32_t*>(sb.prefix);
+    stp.pdis = static_cast<float*>(sb.pdis);
+    stp.ids = ids;
+    stp.D = D;
+    stp.I = I;
+    if (cudaMemsetAsync(sb.ctr, 0, kStCtrBytes, st) != cudaSuccess) return -1;
+    switch (sp.M) {
+        case 16: return st_launch_t<16>(sp, ql, stp, nq, filter_grid, num_sms, st);
+        case 32: return st_launch_t<32>(sp, ql, stp, nq, filter_grid, num_sms, st);
+        case 64: return st_launch_t<64>(sp, ql, stp, nq, filter_grid, num_sms, st);
         default: return -1;
     }
 }

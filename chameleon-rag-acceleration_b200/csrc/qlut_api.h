@@ -21,10 +21,12 @@ struct QlHostParams {
     const float* qscale;
     const float* qamin;
     unsigned long long* counters;   // 3 counters or nullptr
+    const int* guard;               // fallback launch: the kernel runs only if *guard != 0 (nullptr: always)
+    const int* qflag;               // fallback launch with (*guard & 3) == 0: only the queries with qflag[q] != 0
 };
 
 constexpr uint32_t kQlHostMaxList = 1u << 28;
-constexpr size_t kQlGroupBytes = 32;
+constexpr size_t kQlGroupBytes = 48;
 
 bool ql_supported_host(int M, int d, int k);
 // CTAs to launch (resident CTAs per SM x SMs, capped by the number of pairs); 0 when the kernel does not fit
@@ -45,5 +47,27 @@ int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nli
 int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets,
                       const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, cudaStream_t st);
 int ql_launch_scan(const ScanParams& sp, const QlHostParams& qp, int grid, cudaStream_t st);
+
+// ---- streaming pipeline (scan_stream.cuh): bootstrap thresholds -> filter -> exact evaluation -> per-query select ----
+struct StHostBuffers {
+    void* srec;               // max_chunks * 64 * 8 bytes
+    void* sfill;              // max_chunks * 4 bytes
+    unsigned int max_chunks;
+    void* ctr;                // kStCtrBytes, zeroed by st_launch
+    void* slab;               // nq * capq * 8 bytes
+    void* qcnt;               // nq * 4 bytes
+    void* qflag;              // nq * 4 bytes
+    void* qkey;               // nq * 8 bytes
+    int capq;
+    void* prefix;             // nq * nprobe * 4 bytes
+    void* pdis;               // nq * nprobe * 4 bytes
+};
+constexpr size_t kStCtrBytes = 48;
+constexpr int kStChunkRecords = 64;
+int st_filter_grid(int M, int64_t npairs, int num_sms);        // 0: does not fit
+// enqueues the four kernels; the overflow flag (an int, != 0 after an overflow) lives at st_overflow_flag(ctr)
+int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,
+              int64_t* I, int filter_grid, int num_sms, cudaStream_t st);
+const int* st_overflow_flag(const void* ctr);
 
 }  // namespace b200

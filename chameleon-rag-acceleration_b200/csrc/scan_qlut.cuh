@@ -47,7 +47,7 @@ namespace b200 {
 constexpr int kQlQ = 4;                           // queries per work item
 constexpr int kQlPlaneBytes = 256 * 256;          // one table plane: 256 code values x 256-byte rows
 constexpr uint32_t kQlMaxList = 1u << 28;         // survivor entry = (offset << 4) | query mask
-constexpr int kQlSurvCap = 1280;                  // one tile of 1024 codes + the drain trigger
+constexpr int kQlSurvCap = 2304;                  // one tile of 2048 codes + the drain trigger
 constexpr float kQlMagic = 8388608.0f;            // 2^23
 
 template <int M>
@@ -64,11 +64,12 @@ struct QlCfg {
 // work item: up to four (query, probe) pairs of the same list
 struct __align__(16) QlGroup {
     int pair[kQlQ];   // -1: unused slot (always at the end)
+    int query[kQlQ];  // pair / nprobe
     int list;
     uint32_t n;       // list length (> 0)
     int64_t beg;      // first row of the list in codes / ids / snorm
 };
-static_assert(sizeof(QlGroup) == 32, "QlGroup is two 16-byte words");
+static_assert(sizeof(QlGroup) == 48, "QlGroup is three 16-byte words");
 
 struct QlParams {
     // per index
@@ -81,6 +82,8 @@ struct QlParams {
     const float* qscale;      // (nq) s_q
     const float* qamin;       // (nq) lower bound of sum_m min_c A[m][c]
     unsigned long long* counters;   // [0] survivor entries, [1] exact evaluations, [2] work items (may be null)
+    const int* guard;               // fallback launches: run only if *guard != 0 (nullptr: always run)
+    const int* qflag;               // fallback launches with (*guard & 3) == 0: only the queries with qflag[q] != 0
 };
 
 __host__ __device__ inline int ql_topk_cap(int k, int threads) {
@@ -100,12 +103,9 @@ struct QlCtrl {            // 128 bytes
     int work;
     int nsurv[2];          // alternate from one drain to the next (zeroed a whole drain before reuse)
     int cold;
-    float scale[kQlQ];     // s_q
-    float base[kQlQ];      // E - dis0 - amin - sbmin, rounded up
-    float mag[kQlQ];       // |E| + |dis0| + |amin| + |sbmin| (for the rounding slack of thr + base)
-    float astep[kQlQ];     // s_q * sbstep, rounded down
+    float dis0[kQlQ];      // ||r_q||^2, accumulated by the warps that compute the residuals
     int qidx[kQlQ];        // the queries of the work item
-    uint32_t pad_[8];
+    uint32_t pad_[20];
 };
 static_assert(sizeof(QlCtrl) == 128, "QlCtrl is 128 bytes");
 
@@ -376,6 +376,7 @@ __global__ void ql_pair_scatter_kernel(const int32_t* __restrict__ probe, int64_
     order[start[key] + rank] = static_cast<int32_t>(i);
     QlGroup* g = groups + gstart[key] + (rank >> 2);
     g->pair[rank & 3] = static_cast<int32_t>(i);
+    g->query[rank & 3] = static_cast<int32_t>(i / nprobe);
     if ((rank & 3) == 0) {
         g->list = l;
         g->n = static_cast<uint32_t>(sz);
@@ -464,6 +465,7 @@ __device__ __forceinline__ void ql_copy_group_async(QlGroup* dst, const QlGroup*
     const char* s = reinterpret_cast<const char*>(src);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(s) : "memory");
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(s + 16) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 32), "l"(s + 32) : "memory");
 }
 
 // threshold constant of one query in the magic-number domain: a code survives iff !(2^23 + LB > fma(v, -astep, b))
@@ -519,6 +521,20 @@ __device__ __forceinline__ float ql_exact(const uint4 (&cc)[M / 16], const float
     return acc;
 }
 
+// Fold the pending candidates of all Q queues into their best lists.  One out-of-line copy per kernel: the sorting
+// networks are large and run once or twice per work item.  All kT threads call, after a barrier.
+template <int THREADS>
+__device__ __noinline__ void ql_fold_all(unsigned char* tk_base, size_t tk_bytes, int k, int cap, uint4 ext4) {
+    TopK tk[kQlQ];
+    const uint32_t ext[kQlQ] = {ext4.x, ext4.y, ext4.z, ext4.w};
+#pragma unroll
+    for (int q = 0; q < kQlQ; q++) tk[q].bind(tk_base + q * tk_bytes, k, cap);
+    if (!topk_fold_small<THREADS, kQlQ>(tk, ext)) {
+#pragma unroll 1
+        for (int q = 0; q < kQlQ; q++) tk[q].template flush<THREADS>(ext[q]);
+    }
+}
+
 template <int M>
 __global__ void __launch_bounds__(QlCfg<M>::kT, M == 64 ? 1 : 2)   // M = 64: one CTA per SM (128 KB of tables), 255 registers
 scan_qlut_kernel(const ScanParams p, const QlParams ql) {
@@ -545,8 +561,11 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
     const bool x8 = (r & 8) != 0, x4 = (r & 4) != 0;
     // byte (p ^ (r & 3)) of a word: selectors 3210, 2301, 1032, 0123
     const uint32_t bsel = (r & 3) == 0 ? 0x3210u : (r & 3) == 1 ? 0x2301u : (r & 3) == 2 ? 0x1032u : 0x0123u;
+    const int ovf = ql.guard ? *reinterpret_cast<const volatile int*>(ql.guard) : 3;
+    if (ovf == 0) return;                                                            // fallback launch, not needed
     const int ngroups = p.stats->ngroups;
     const int dsub = p.dsub;
+    int* const work_counter = ql.guard ? &p.stats->work_counter2 : &p.stats->work_counter;
     // cold start: that many survivors are evaluated before the first thresholds exist
     const int kBoot = min(kT, (p.k + 31) & ~31);
     unsigned long long n_surv = 0ull, n_exact = 0ull, n_items = 0ull;   // thread 0's copies are reported
@@ -555,18 +574,20 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
     if (tid == 0) {
         ctrl->nsurv[0] = 0;
         ctrl->nsurv[1] = 0;
-        next_work = atomicAdd(&p.stats->work_counter, 1);
+        next_work = atomicAdd(work_counter, 1);
         if (next_work < ngroups) ql_copy_group_async(&s_grp[0], static_cast<const QlGroup*>(p.groups) + next_work);
     }
     for (;;) {
         if (tid == 0) {
             ctrl->work = next_work;
+#pragma unroll
+            for (int q = 0; q < Q; q++) ctrl->dis0[q] = 0.0f;
             asm volatile("cp.async.wait_all;" ::: "memory");
         }
         __syncthreads();
         const int wk = ctrl->work;
         if (wk >= ngroups) break;
-        if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
+        if (tid == 0) next_work = atomicAdd(work_counter, 1);
         const QlGroup grp = s_grp[buf];
         int pair[Q], qi[Q];
         uint32_t vmask = 0u;
@@ -574,29 +595,57 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
         for (int q = 0; q < Q; q++) {
             const bool has = grp.pair[q] >= 0;
             pair[q] = has ? grp.pair[q] : grp.pair[0];
-            qi[q] = pair[q] / p.nprobe;
+            qi[q] = has ? grp.query[q] : grp.query[0];
             vmask |= has ? (1u << q) : 0u;
+        }
+        if ((ovf & 3) == 0) {
+            // fallback after slab overflows: only the flagged queries are recomputed (CTA-uniform decision)
+#pragma unroll
+            for (int q = 0; q < Q; q++)
+                if (((vmask >> q) & 1u) && __ldg(ql.qflag + qi[q]) == 0) vmask &= ~(1u << q);
+            if (vmask == 0u) {
+                buf ^= 1;
+                if (tid == 0 && next_work < ngroups)
+                    ql_copy_group_async(&s_grp[buf], static_cast<const QlGroup*>(p.groups) + next_work);
+                continue;
+            }
         }
         const int list = grp.list;
         const uint32_t n = grp.n;
         const uint4* lp = reinterpret_cast<const uint4*>(p.codes + grp.beg * M);
         const uint16_t* sp = ql.snorm + grp.beg;
 
-        uint32_t ext[Q];
-#pragma unroll
-        for (int q = 0; q < Q; q++) ext[q] = *reinterpret_cast<volatile uint32_t*>(p.qthr + qi[q]);
+        // ONE thread reads each query's current threshold (other CTAs lower it concurrently): every thread must see
+        // the same value, the control flow below depends on it
 #pragma unroll
         for (int q = 0; q < Q; q++)
             if (tid == q) {
-                tk[q].reset(ext[q]);
+                tk[q].reset(*reinterpret_cast<volatile uint32_t*>(p.qthr + qi[q]));
                 ctrl->qidx[q] = qi[q];
             }
 
-        // a2: residuals r = fl(q - c), kept for the exact evaluation of the survivors
-        for (int e = tid; e < Q * p.d; e += kT) {
-            const int q = e / p.d, j = e - q * p.d;
-            res[q * rstride + j] = __fsub_rn(__ldg(p.xq + static_cast<int64_t>(qi[q]) * p.d + j),
-                                             __ldg(p.cent + static_cast<int64_t>(list) * p.d + j));
+        // a2: residuals r = fl(q - c), kept for the exact evaluation of the survivors; ||r||^2 summed on the way (any
+        // order: only a bound is needed)
+        {
+            float n2[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) n2[q] = 0.0f;
+            for (int j = tid; j < p.d; j += kT) {
+                const float cj = __ldg(p.cent + static_cast<int64_t>(list) * p.d + j);
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const float rj = __fsub_rn(__ldg(p.xq + static_cast<int64_t>(qi[q]) * p.d + j), cj);
+                    res[q * rstride + j] = rj;
+                    n2[q] = fmaf(rj, rj, n2[q]);
+                }
+            }
+            if (wid * 32 < p.d) {   // warps that hold a part of the residuals
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    for (int o = 16; o > 0; o >>= 1) n2[q] += __shfl_xor_sync(0xffffffffu, n2[q], o);
+                    if (lane == 0) atomicAdd(&ctrl->dis0[q], n2[q]);
+                }
+            }
         }
         // the four queries' tables, interleaved entry-wise: row c of chunk h = 16 slots x (u_q0, u_q1, u_q2, u_q3).
         // Eight lanes cover the eight slot pairs of one row (128 contiguous bytes: conflict-free STS.128), four rows
@@ -629,39 +678,38 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
                 }
             }
         }
-        __syncthreads();
-        // pair constants: warp q sums ||r_q||^2 (any order: only a bound is needed)
-        if (wid < Q) {
-            const int q = wid;
-            float a = 0.0f;
-            for (int j = lane; j < p.d; j += 32) a = fmaf(res[q * rstride + j], res[q * rstride + j], a);
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) {
-                const float dis0 = a * (1.0f - static_cast<float>(p.d + 5) * 5.9604645e-8f);
-                const float rn = sqrtf(a) * 1.00001f + ql.pmax;
-                const float E = static_cast<float>(dsub + M + 8) * 5.9604645e-8f * rn * rn * 1.00001f;
-                const float am = __ldg(ql.qamin + qi[q]), sm = __ldg(ql.sbmin + list), st = __ldg(ql.sbstep + list);
-                const float s = __ldg(ql.qscale + qi[q]);
-                const float mag = fabsf(E) + fabsf(dis0) + fabsf(am) + fabsf(sm);
-                ctrl->scale[q] = s;
-                ctrl->base[q] = (((E - dis0) - am) - sm) + 4.8e-7f * mag;
-                ctrl->mag[q] = mag;
-                ctrl->astep[q] = s * st * 0.999999f;
-            }
+        // pair constants (loads issued before the barrier)
+        float c_am[Q], c_s[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            c_am[q] = __ldg(ql.qamin + qi[q]);
+            c_s[q] = __ldg(ql.qscale + qi[q]);
         }
+        const float c_sm = __ldg(ql.sbmin + list), c_st = __ldg(ql.sbstep + list);
         __syncthreads();
+        float c_base[Q], c_mag[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const float a = ctrl->dis0[q];
+            const float dis0 = a * (1.0f - static_cast<float>(p.d + 5) * 5.9604645e-8f);
+            const float rn = sqrtf(a) * 1.00001f + ql.pmax;
+            const float E = static_cast<float>(dsub + M + 8) * 5.9604645e-8f * rn * rn * 1.00001f;
+            c_mag[q] = fabsf(E) + fabsf(dis0) + fabsf(c_am[q]) + fabsf(c_sm);
+            c_base[q] = (((E - dis0) - c_am[q]) - c_sm) + 4.8e-7f * c_mag[q];
+        }
         buf ^= 1;
         if (tid == 0 && next_work < ngroups)
             ql_copy_group_async(&s_grp[buf], static_cast<const QlGroup*>(p.groups) + next_work);
 
         float na[Q], tb[Q];   // -astep and the threshold constant of every query (per-thread copies)
-        uint32_t th[Q];
+        uint32_t th[Q], ext[Q];
         bool cold = false;
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            na[q] = -ctrl->astep[q];
-            th[q] = ext[q];
-            tb[q] = (vmask >> q) & 1u ? ql_threshold_const(th[q], ctrl->scale[q], ctrl->base[q], ctrl->mag[q]) : -INFINITY;
+            na[q] = -(c_s[q] * c_st * 0.999999f);
+            th[q] = tk[q].threshold();
+            ext[q] = th[q];
+            tb[q] = (vmask >> q) & 1u ? ql_threshold_const(th[q], c_s[q], c_base[q], c_mag[q]) : -INFINITY;
             cold = cold || (((vmask >> q) & 1u) && th[q] >= kInfBits);
         }
         int sphase = 0;
@@ -711,17 +759,12 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
             for (int q = 0; q < Q; q++) {
                 th[q] = tk[q].threshold();
                 ext[q] = th[q];
-                tb[q] = (vmask >> q) & 1u ? ql_threshold_const(th[q], ctrl->scale[q], ctrl->base[q], ctrl->mag[q]) : -INFINITY;
+                tb[q] = (vmask >> q) & 1u ? ql_threshold_const(th[q], c_s[q], c_base[q], c_mag[q]) : -INFINITY;
                 c = c || (((vmask >> q) & 1u) && th[q] >= kInfBits);
             }
             cold = c;
         };
-        auto fold_all = [&]() {
-            if (!topk_fold_small<kT, Q>(tk, ext)) {
-#pragma unroll
-                for (int q = 0; q < Q; q++) tk[q].template flush<kT>(ext[q]);
-            }
-        };
+        auto fold_all = [&]() { ql_fold_all<kT>(tk_base, tk_bytes, p.k, kCap, make_uint4(ext[0], ext[1], ext[2], ext[3])); };
         // Exact evaluation of the queued survivors; folds the candidate queues and refreshes the thresholds.  Called by
         // all threads (CTA-uniform), right after a barrier.  While some query has no threshold yet, everything passes the
         // filter: then only kBoot entries are evaluated first, and the rest is filtered AGAIN with the thresholds that
@@ -769,10 +812,7 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
                     bool over = false;
 #pragma unroll
                     for (int q = 0; q < Q; q++) over = over || tk[q].pending() > kCap - kT;
-                    if (__syncthreads_or(over) && base < ns) {
-#pragma unroll
-                        for (int q = 0; q < Q; q++) tk[q].template flush<kT>(ext[q]);
-                    }
+                    if (__syncthreads_or(over) && base < ns) fold_all();
                 }
             }
             if (tid == 0) ctrl->nsurv[sphase] = 0;   // next used after the NEXT drain: several barriers from now
@@ -783,22 +823,13 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
             }
         };
 
-        // a4: the filter.  Block b = codes b*kT + tid.
+        // a4: the filter.  Block b = codes b*kT + tid.  Chunks of eight blocks (one while some query has no threshold
+        // yet), then a CTA-wide check: drain once enough survivors are waiting (tight thresholds early are worth more
+        // than fewer drains), and always after the last block.
         const uint32_t nblk = (n + kT - 1) / kT;
         uint32_t blk = 0;
-        // cold start: one block at a time, drained immediately
-        while (cold && blk < nblk) {
-            const uint32_t idx = blk * kT + tid;
-            const QlCode<M> c = ql_load_code<M>(lp, sp, idx, n);
-            const uint32_t m = test(c);
-            enqueue(idx < n && m != 0u, (idx << 4) | m);
-            blk++;
-            __syncthreads();
-            drain();
-        }
-        if (blk < nblk) {
-            QlCode<M> c0 = ql_load_code<M>(lp, sp, blk * kT + tid, n), c1 = ql_load_code<M>(lp, sp, (blk + 1) * kT + tid, n),
-                      c2, c3;
+        bool primed = false;
+        QlCode<M> c0, c1, c2, c3;
 #define QL_ITER(CUR, LOADTO, TB)                                                                     \
     {                                                                                                \
         LOADTO = ql_load_code<M>(lp, sp, base + (TB + 2) * kT, n);                                   \
@@ -806,19 +837,34 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
         const uint32_t m_ = test(CUR);                                                               \
         enqueue(idx < n && m_ != 0u, (idx << 4) | m_);                                               \
     }
-            // drain once enough survivors are waiting (tight thresholds early are worth more than fewer drains), and
-            // always after the last block
-            for (uint32_t t0 = blk; t0 < nblk; t0 += 4) {
-                const uint32_t base = t0 * kT + tid;
-                QL_ITER(c0, c2, 0)
-                if (t0 + 1 < nblk) QL_ITER(c1, c3, 1)
-                if (t0 + 2 < nblk) QL_ITER(c2, c0, 2)
-                if (t0 + 3 < nblk) QL_ITER(c3, c1, 3)
-                const int seen = *reinterpret_cast<volatile int*>(&ctrl->nsurv[sphase]);
-                if (__syncthreads_or(seen > p.quad_drain_at) || t0 + 4 >= nblk) drain();
+#pragma unroll 1
+        while (blk < nblk) {
+            if (cold) {
+                const uint32_t idx = blk * kT + tid;
+                const QlCode<M> c = ql_load_code<M>(lp, sp, idx, n);
+                const uint32_t m = test(c);
+                enqueue(idx < n && m != 0u, (idx << 4) | m);
+                blk++;
+                primed = false;
+            } else {
+                if (!primed) {
+                    c0 = ql_load_code<M>(lp, sp, blk * kT + tid, n);
+                    c1 = ql_load_code<M>(lp, sp, (blk + 1) * kT + tid, n);
+                    primed = true;
+                }
+#pragma unroll 1
+                for (int rnd = 0; rnd < 2 && blk < nblk; rnd++, blk += 4) {
+                    const uint32_t base = blk * kT + tid;
+                    QL_ITER(c0, c2, 0)
+                    if (blk + 1 < nblk) QL_ITER(c1, c3, 1)
+                    if (blk + 2 < nblk) QL_ITER(c2, c0, 2)
+                    if (blk + 3 < nblk) QL_ITER(c3, c1, 3)
+                }
             }
-#undef QL_ITER
+            const int seen = *reinterpret_cast<volatile int*>(&ctrl->nsurv[sphase]);
+            if (__syncthreads_or(seen > (cold ? 0 : p.quad_drain_at)) || blk >= nblk) drain();
         }
+#undef QL_ITER
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             if (vmask & (1u << q)) {

@@ -1,0 +1,565 @@
+// scan_stream.cuh -- the per-query-table filter (scan_qlut.cuh) as a STREAMING pipeline: no top-k inside the scan.
+//
+// Why.  scan_qlut_kernel evaluates its survivors and folds its top-k lists inside every work item: a chain of
+// dependent phases (queue -> barrier -> a few lanes walk the codebook -> barrier -> fold -> barrier -> publish) that
+// costs ~10 us per item whatever the list length.  On an 8-way vector shard (1.5k-code lists) that chain, not the
+// scan, is the run time (ncu: 35 % issue slots, barrier and long-scoreboard stalls on top).
+//
+// How.  Everything that was serial inside an item becomes its own fully parallel kernel:
+//   S  st_boot_kernel    one CTA per query: scan positions (prefix of list sizes in probe order), ||q - c||^2 of every
+//                        probed list, and a BOOTSTRAP THRESHOLD: of the first <= 2048 codes in scan order (the nearest
+//                        lists), the candidates with the smallest estimated distance are evaluated exactly; their k-th
+//                        smallest exact distance bounds the query's final k-th distance from above;
+//   A  st_filter_kernel  persistent CTAs over (list, <= 4 queries) work items: copy the queries' tables, scan the list
+//                        with the FIXED thresholds, append survivors to a global record buffer.  Two barriers per item,
+//                        no top-k state, no exact arithmetic; every warp owns a 64-record chunk at a time, so an append
+//                        is a coalesced store and one global atomic per 64 survivors;
+//   B  st_eval_kernel    one thread per survivor: exact distance in the oracle's operation order (residual formed on
+//                        the fly), kept if <= the threshold: key = (distance bits << 32) | scan position, appended to
+//                        the query's slab;
+//   C  st_select_kernel  one CTA per query: the k smallest keys of the slab = the oracle's (distance, probe rank,
+//                        offset) order; id lookup.
+// The result is exactly the oracle's: the threshold is the k-th smallest of k real distances (so the true top-k lies at
+// or below it), the filter never drops a code whose exact distance is <= the threshold (scan_qlut.cuh's bound), and every
+// kept code is evaluated exactly.
+// Buffers are sized for the typical survivor rate.  If the record buffer overflows (degenerate data, fewer than k
+// vectors in the probed lists) a flag is raised on the device and the guarded launches that follow -- scan_qlut_kernel
+// and merge_query_kernel over the same work items -- recompute the batch; if only a query's slab overflows (hundreds of
+// duplicate codes at its k-th distance) they recompute that query alone; they return at once otherwise.
+#pragma once
+#include "scan_qlut.cuh"
+
+namespace b200 {
+
+constexpr int kStChunk = 64;          // survivor records per chunk
+constexpr int kStBootCodes = 2048;    // codes (in scan order) the bootstrap looks at
+constexpr int kStBootThreads = 256;
+constexpr int kStSelCap = 2048;
+
+struct StCounters {
+    unsigned int nchunks;             // chunks handed out
+    int overflow;                     // != 0: the fallback launches recompute the batch (1: scan positions exceed 32 bits,
+                                      // 2: record buffer full, 4: a query's slab full)
+    unsigned long long records;       // statistics: survivor records, exact evaluations
+    unsigned long long evals;
+    unsigned long long kept;          // keys admitted to the slabs
+    unsigned int maxkept;             // largest slab
+    unsigned int nflag;               // queries answered by the fallback launches
+};
+
+struct StParams {
+    uint2* srec;                      // (max_chunks * 64) survivor records: (work item, (offset << 4) | query mask)
+    unsigned int* sfill;              // (max_chunks) records in each chunk
+    unsigned int max_chunks;
+    StCounters* ctr;
+    uint64_t* slab;                   // (nq, capq) keys of the codes at or below the query's threshold
+    unsigned int* qcnt;               // (nq)
+    int* qflag;                       // (nq) != 0: the query's slab overflowed, the fallback launches answer it
+    uint64_t* qkey;                   // (nq) bootstrap threshold as a full key (distance bits, scan position): keys are
+                                      // distinct, so duplicate codes at the k-th distance cannot flood a slab
+    int capq;
+    uint32_t* prefix;                 // (nq, nprobe) scan position of the first code of every probed list
+    float* pdis;                      // (nq, nprobe) ||fl(q - c)||^2
+    const int64_t* ids;
+    float* D;                         // (nq, k)
+    int64_t* I;
+};
+
+__host__ __device__ inline int st_boot_nsel(int k) {
+    const int n = 4 * k;
+    return n < 32 ? 32 : n > 1024 ? 1024 : n;
+}
+__host__ __device__ inline size_t st_boot_smem(int d, int M, int nprobe, int k) {
+    // query | the query's table | list sizes | prefix | list ids | TopK
+    return sizeof(float) * ((d + 3) & ~3) + sizeof(uint16_t) * 256 * M + 3 * sizeof(uint32_t) * nprobe +
+           TopK::smem_bytes(st_boot_nsel(k), kStSelCap) + 64;
+}
+
+// exact distance with the residual formed on the fly: r_j = fl(q_j - c_j), then the oracle's sums
+template <int M>
+__device__ __forceinline__ float st_exact(const uint8_t* __restrict__ code, const float* __restrict__ q,
+                                          const float* __restrict__ c, const float* __restrict__ pq, int dsub) {
+    float acc = 0.0f;
+#pragma unroll 1
+    for (int m0 = 0; m0 < M; m0 += 4) {
+        const uint32_t cw = __ldg(reinterpret_cast<const uint32_t*>(code + m0));
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = m0 + b;
+            const uint32_t cv = (cw >> (8 * b)) & 255u;
+            const float* pc = pq + (static_cast<int64_t>(m) * 256 + cv) * dsub;
+            const float* qq = q + m * dsub;
+            const float* cc = c + m * dsub;
+            float t = 0.0f;
+            if ((dsub & 3) == 0) {
+                for (int j = 0; j < dsub; j += 4) {
+                    const float4 pv = __ldg(reinterpret_cast<const float4*>(pc + j));
+                    const float4 qv = *reinterpret_cast<const float4*>(qq + j);
+                    const float4 cv4 = __ldg(reinterpret_cast<const float4*>(cc + j));
+                    t = sqdiff_acc(t, __fsub_rn(qv.x, cv4.x), pv.x);
+                    t = sqdiff_acc(t, __fsub_rn(qv.y, cv4.y), pv.y);
+                    t = sqdiff_acc(t, __fsub_rn(qv.z, cv4.z), pv.z);
+                    t = sqdiff_acc(t, __fsub_rn(qv.w, cv4.w), pv.w);
+                }
+            } else {
+                for (int j = 0; j < dsub; j++) t = sqdiff_acc(t, __fsub_rn(qq[j], __ldg(cc + j)), __ldg(pc + j));
+            }
+            acc = __fadd_rn(acc, t);
+        }
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// S: per query -- scan positions, coarse distances, bootstrap threshold
+// ------------------------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(kStBootThreads)
+st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, const float* __restrict__ pq,
+               const int64_t* __restrict__ offsets, const uint8_t* __restrict__ codes,
+               const int32_t* __restrict__ probe, int nprobe, int d, int dsub, int k, QlParams ql, StParams st,
+               uint32_t* __restrict__ qthr) {
+    extern __shared__ __align__(16) unsigned char smem_boot[];
+    const int dpad = (d + 3) & ~3;
+    float* qv = reinterpret_cast<float*>(smem_boot);
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(qv + dpad);                 // [256][M] the query's table
+    uint32_t* s_sz = reinterpret_cast<uint32_t*>(s_lut + 256 * M);
+    uint32_t* s_pre = s_sz + nprobe;
+    int32_t* s_list = reinterpret_cast<int32_t*>(s_pre + nprobe);
+    const int nsel = st_boot_nsel(k);
+    uintptr_t tkp = (reinterpret_cast<uintptr_t>(s_list + nprobe) + 7) & ~static_cast<uintptr_t>(7);
+    TopK tk;
+    tk.bind(reinterpret_cast<void*>(tkp), nsel, kStSelCap);
+    __shared__ unsigned long long s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t q = blockIdx.x;
+    for (int j = tid; j < d; j += kStBootThreads) qv[j] = xq[q * d + j];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(ql.qlut + q * 256 * M);
+        uint4* dst = reinterpret_cast<uint4*>(s_lut);
+        for (int i = tid; i < 256 * M / 8; i += kStBootThreads) dst[i] = __ldg(src + i);
+    }
+    for (int r = tid; r < nprobe; r += kStBootThreads) {
+        const int l = probe[q * nprobe + r];
+        int64_t sz = 0;
+        if (l >= 0) sz = offsets[l + 1] - offsets[l];
+        s_list[r] = sz > 0 ? l : -1;
+        s_sz[r] = static_cast<uint32_t>(sz > 0 ? sz : 0);
+    }
+    if (tid == 0) tk.reset(kInfBits);
+    __syncthreads();
+    // scan positions: exclusive prefix of the list sizes in probe order (warp 0, 32 ranks at a time)
+    if (wid == 0) {
+        unsigned long long carry = 0ull;
+        for (int r0 = 0; r0 < nprobe; r0 += 32) {
+            const int r = r0 + lane;
+            const unsigned long long v = r < nprobe ? s_sz[r] : 0u;
+            unsigned long long x = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (r < nprobe) {
+                const unsigned long long pre = carry + x - v;
+                s_pre[r] = static_cast<uint32_t>(pre);
+                st.prefix[q * nprobe + r] = static_cast<uint32_t>(pre);
+            }
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) {
+            s_total = carry;
+            if (carry >= (1ull << 32)) atomicOr(&st.ctr->overflow, 1);   // scan positions do not fit 32 bits: fallback
+            st.qcnt[q] = 0u;
+            st.qflag[q] = 0;
+        }
+    }
+    // coarse distances of every probed list (any summation order: only a bound is needed)
+    for (int r = wid; r < nprobe; r += kStBootThreads / 32) {
+        const int l = s_list[r];
+        float a = 0.0f;
+        if (l >= 0) {
+            for (int j = lane; j < d; j += 32) {
+                const float rj = __fsub_rn(qv[j], __ldg(cent + static_cast<int64_t>(l) * d + j));
+                a = fmaf(rj, rj, a);
+            }
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        }
+        if (lane == 0) st.pdis[q * nprobe + r] = a;
+    }
+    __syncthreads();
+    // candidates: the first codes in scan order, ranked by the estimated distance dis0 + SB + sum_m A; all of them
+    // go to the queue (it holds kStBootCodes keys), one fold at the end
+    const uint32_t ncand = static_cast<uint32_t>(s_total < kStBootCodes ? s_total : kStBootCodes);
+    const float sq = ql.qscale[q], aq = ql.qamin[q];
+    const float inv = sq > 0.0f ? 1.0f / sq : 0.0f;
+    constexpr int kPer = kStBootCodes / kStBootThreads;   // 8 candidates per thread, their loads in flight together
+    constexpr int kBatch = M == 16 ? 8 : M == 32 ? 4 : 2;
+#pragma unroll 1
+    for (int i0 = 0; i0 < kPer; i0 += kBatch) {
+        uint4 cv[kBatch][M / 16];
+        float add[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; i++) {
+            const uint32_t pos = (i0 + i) * kStBootThreads + tid;
+            add[i] = 0.0f;
+#pragma unroll
+            for (int h = 0; h < M / 16; h++) cv[i][h] = make_uint4(0u, 0u, 0u, 0u);
+            if (pos < ncand) {
+                int r = 0;
+                while (r + 1 < nprobe && s_pre[r + 1] <= pos) r++;       // last rank whose first position is <= pos
+                const int l = s_list[r];
+                const int64_t row = offsets[l] + (pos - s_pre[r]);
+                const uint4* cp = reinterpret_cast<const uint4*>(codes + row * M);
+#pragma unroll
+                for (int h = 0; h < M / 16; h++) cv[i][h] = __ldg(cp + h);
+                add[i] = st.pdis[q * nprobe + r] + __ldg(ql.sbmin + l) +
+                         __ldg(ql.sbstep + l) * static_cast<float>(__ldg(ql.snorm + row)) + aq;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; i++) {
+            const uint32_t pos = (i0 + i) * kStBootThreads + tid;
+            uint32_t u = 0u;
+#pragma unroll
+            for (int h = 0; h < M / 16; h++) {
+                const uint32_t w[4] = {cv[i][h].x, cv[i][h].y, cv[i][h].z, cv[i][h].w};
+#pragma unroll
+                for (int mm = 0; mm < 16; mm++)
+                    u += s_lut[((w[mm >> 2] >> (8 * (mm & 3))) & 255u) * M + 16 * h + mm];
+            }
+            const float est = add[i] + static_cast<float>(u) * inv;
+            uint32_t bits = __float_as_uint(fmaxf(est, 0.0f));
+            if (!(est == est)) bits = 0x7f7fffffu;                    // NaN estimates rank last
+            tk.push(pos < ncand, make_key(bits, pos));
+        }
+    }
+    __syncthreads();
+    tk.flush<kStBootThreads>(kInfBits);
+    // exact distances of the selected candidates; their k-th smallest is the threshold
+    const int ns = tk.count();
+    uint64_t mine[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int i = tid + u * kStBootThreads;
+        mine[u] = kPadKey;
+        if (i < ns) {
+            const uint32_t pos = static_cast<uint32_t>(tk.sorted()[i] & 0xffffffffu);
+            int r = 0;
+            while (r + 1 < nprobe && s_pre[r + 1] <= pos) r++;
+            const int l = s_list[r];
+            const int64_t row = offsets[l] + (pos - s_pre[r]);
+            const uint32_t b = __float_as_uint(st_exact<M>(codes + row * M, qv, cent + static_cast<int64_t>(l) * d, pq, dsub));
+            mine[u] = make_key(b, pos);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) tk.reset(kInfBits);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; u++) tk.push(mine[u] != kPadKey, mine[u]);
+    __syncthreads();
+    tk.flush<kStBootThreads>(kInfBits);
+    if (tid == 0) {
+        uint32_t t = kInfBits;
+        uint64_t tkey = kPadKey;
+        if (tk.count() >= k) {
+            const uint64_t key = tk.sorted()[k - 1];
+            if (static_cast<uint32_t>(key >> 32) < kInfBits) {
+                t = static_cast<uint32_t>(key >> 32);
+                tkey = key;
+            }
+        }
+        qthr[q] = t;
+        st.qkey[q] = tkey;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A: the filter
+// ------------------------------------------------------------------------------------------------------------------
+struct StCtrl {            // 32 bytes
+    int work;
+    int pad_[7];
+};
+
+template <int M>
+__host__ __device__ inline size_t st_filter_smem() {
+    return static_cast<size_t>(QlCfg<M>::kLutBytes) + sizeof(StCtrl) + 2 * sizeof(QlGroup);
+}
+
+template <int M>
+__global__ void __launch_bounds__(QlCfg<M>::kT, M == 64 ? 1 : 3)
+st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
+    using Cfg = QlCfg<M>;
+    constexpr int kT = Cfg::kT;
+    constexpr int Q = kQlQ;
+    extern __shared__ __align__(1024) unsigned char smem_st[];
+    char* lutb = reinterpret_cast<char*>(smem_st);
+    StCtrl* ctrl = reinterpret_cast<StCtrl*>(smem_st + Cfg::kLutBytes);
+    QlGroup* s_grp = reinterpret_cast<QlGroup*>(ctrl + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r = lane & 15;
+    const QlOffsets offs = ql_make_offsets(r);
+    const bool x8 = (r & 8) != 0, x4 = (r & 4) != 0;
+    const uint32_t bsel = (r & 3) == 0 ? 0x3210u : (r & 3) == 1 ? 0x2301u : (r & 3) == 2 ? 0x1032u : 0x0123u;
+    const int ngroups = p.stats->ngroups;
+    const int dsub = p.dsub;
+    // this warp's open chunk of the survivor buffer (warp-uniform)
+    unsigned int chunk = 0xffffffffu, fill = 0u, nrec = 0u;
+    bool dead = false;
+
+    int next_work = 0, buf = 0;
+    if (tid == 0) {
+        next_work = atomicAdd(&p.stats->work_counter, 1);
+        if (next_work < ngroups) ql_copy_group_async(&s_grp[0], static_cast<const QlGroup*>(p.groups) + next_work);
+    }
+    for (;;) {
+        if (tid == 0) {
+            ctrl->work = next_work;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        __syncthreads();   // also: every warp is done with the previous item's tables
+        const int wk = ctrl->work;
+        if (wk >= ngroups) break;
+        if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
+        const QlGroup grp = s_grp[buf];
+        int qi[Q];
+        uint32_t vmask = 0u;
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const bool has = grp.pair[q] >= 0;
+            qi[q] = has ? grp.query[q] : grp.query[0];
+            vmask |= has ? (1u << q) : 0u;
+        }
+        const int list = grp.list;
+        const uint32_t n = grp.n;
+        const uint4* lp = reinterpret_cast<const uint4*>(p.codes + grp.beg * M);
+        const uint16_t* sp = ql.snorm + grp.beg;
+        // first codes in flight before the set-up work
+        QlCode<M> c0 = ql_load_code<M>(lp, sp, tid, n), c1 = ql_load_code<M>(lp, sp, kT + tid, n), c2, c3;
+        // pair constants (every thread computes its own copy)
+        float na[Q], tb[Q];
+        {
+            const float c_sm = __ldg(ql.sbmin + list), c_st = __ldg(ql.sbstep + list);
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const int pr = (vmask >> q) & 1u ? grp.pair[q] : grp.pair[0];
+                const float a = __ldg(st.pdis + pr);
+                const float c_am = __ldg(ql.qamin + qi[q]), c_s = __ldg(ql.qscale + qi[q]);
+                const uint32_t thr = __ldg(p.qthr + qi[q]);
+                const float dis0 = a * (1.0f - static_cast<float>(p.d + 5) * 5.9604645e-8f);
+                const float rn = sqrtf(a) * 1.00001f + ql.pmax;
+                const float E = static_cast<float>(dsub + M + 8) * 5.9604645e-8f * rn * rn * 1.00001f;
+                const float mag = fabsf(E) + fabsf(dis0) + fabsf(c_am) + fabsf(c_sm);
+                const float base = (((E - dis0) - c_am) - c_sm) + 4.8e-7f * mag;
+                na[q] = -(c_s * c_st * 0.999999f);
+                tb[q] = (vmask >> q) & 1u ? ql_threshold_const(thr, c_s, base, mag) : -INFINITY;
+            }
+        }
+        // the four queries' tables, interleaved entry-wise (see scan_qlut_kernel)
+        {
+            const int sp2 = lane & 7;
+            constexpr int kSteps = Cfg::kChunks * 64 / (kT / 32);
+#pragma unroll 1
+            for (int i0 = 0; i0 < kSteps; i0 += 8) {
+                uint32_t a[8][Q];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int it = wid + (i0 + i) * (kT / 32);
+                    const int h = it >> 6, row = ((it & 63) << 2) + (lane >> 3);
+#pragma unroll
+                    for (int q = 0; q < Q; q++)
+                        a[i][q] = __ldg(reinterpret_cast<const uint32_t*>(ql.qlut + (static_cast<int64_t>(qi[q]) * 256 + row) * M) +
+                                        h * 8 + sp2);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int it = wid + (i0 + i) * (kT / 32);
+                    const int h = it >> 6, row = ((it & 63) << 2) + (lane >> 3);
+                    uint4 e;
+                    e.x = __byte_perm(a[i][0], a[i][1], 0x5410);
+                    e.y = __byte_perm(a[i][2], a[i][3], 0x5410);
+                    e.z = __byte_perm(a[i][0], a[i][1], 0x7632);
+                    e.w = __byte_perm(a[i][2], a[i][3], 0x7632);
+                    *reinterpret_cast<uint4*>(lutb + (h >> 1) * kQlPlaneBytes + row * 256 + (h & 1) * 128 + sp2 * 16) = e;
+                }
+            }
+        }
+        __syncthreads();
+        buf ^= 1;
+        if (tid == 0 && next_work < ngroups)
+            ql_copy_group_async(&s_grp[buf], static_cast<const QlGroup*>(p.groups) + next_work);
+
+        auto test = [&](const QlCode<M>& c) -> uint32_t {
+            uint2 lb = ql_block16(lutb, c.v[0], x8, x4, bsel, offs);
+#pragma unroll
+            for (int h = 1; h < M / 16; h++) {
+                const uint2 t_ = ql_block16(lutb + (h >> 1) * kQlPlaneBytes + (h & 1) * 128, c.v[h], x8, x4, bsel, offs);
+                lb.x += t_.x;
+                lb.y += t_.y;
+            }
+            const float vs = static_cast<float>(c.s);
+            const float f0 = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7410)),
+                        f1 = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7432)),
+                        f2 = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7410)),
+                        f3 = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7432));
+            const bool h0 = !(f0 > fmaf(vs, na[0], tb[0])), h1 = !(f1 > fmaf(vs, na[1], tb[1])),
+                       h2 = !(f2 > fmaf(vs, na[2], tb[2])), h3 = !(f3 > fmaf(vs, na[3], tb[3]));
+            return (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u);
+        };
+        // survivors go straight to this warp's chunk of the global record buffer
+        auto append = [&](bool hit, uint32_t entry) {
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal == 0u || dead) return;
+            const unsigned np = __popc(bal);
+            if (chunk == 0xffffffffu || fill + np > kStChunk) {
+                unsigned int c = 0u;
+                if (lane == 0) {
+                    if (chunk != 0xffffffffu) st.sfill[chunk] = fill;
+                    c = atomicAdd(&st.ctr->nchunks, 1u);
+                }
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= st.max_chunks) {
+                    if (lane == 0) atomicOr(&st.ctr->overflow, 2);
+                    dead = true;
+                    chunk = 0xffffffffu;
+                    return;
+                }
+                chunk = c;
+                fill = 0u;
+            }
+            if (hit) st.srec[static_cast<size_t>(chunk) * kStChunk + fill + __popc(bal & lanemask_lt())] =
+                         make_uint2(static_cast<uint32_t>(wk), entry);
+            fill += np;
+            nrec += np;
+        };
+
+        const uint32_t nblk = (n + kT - 1) / kT;
+#define ST_ITER(CUR, LOADTO, TB)                                                                     \
+    {                                                                                                \
+        LOADTO = ql_load_code<M>(lp, sp, base + (TB + 2) * kT, n);                                   \
+        const uint32_t idx = base + TB * kT;                                                         \
+        const uint32_t m_ = test(CUR);                                                               \
+        append(idx < n && m_ != 0u, (idx << 4) | m_);                                                \
+    }
+#pragma unroll 1
+        for (uint32_t t0 = 0; t0 < nblk; t0 += 4) {
+            const uint32_t base = t0 * kT + tid;
+            ST_ITER(c0, c2, 0)
+            if (t0 + 1 < nblk) ST_ITER(c1, c3, 1)
+            if (t0 + 2 < nblk) ST_ITER(c2, c0, 2)
+            if (t0 + 3 < nblk) ST_ITER(c3, c1, 3)
+        }
+#undef ST_ITER
+    }
+    if (lane == 0) {
+        if (chunk != 0xffffffffu) st.sfill[chunk] = fill;
+        if (nrec) atomicAdd(&st.ctr->records, static_cast<unsigned long long>(nrec));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// B: exact evaluation of the survivors
+// ------------------------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256)
+st_eval_kernel(const ScanParams p, const StParams st) {
+    const unsigned int nchunks = min(st.ctr->nchunks, st.max_chunks);
+    const int tid = threadIdx.x;
+    unsigned long long nev = 0ull;
+    for (unsigned int c0 = blockIdx.x * 4u; c0 < nchunks; c0 += gridDim.x * 4u) {
+        const unsigned int c = c0 + (tid >> 6);
+        const unsigned int slot = tid & 63;
+        if (c >= nchunks || slot >= st.sfill[c]) continue;
+        const uint2 rec = st.srec[static_cast<size_t>(c) * kStChunk + slot];
+        const QlGroup* g = static_cast<const QlGroup*>(p.groups) + rec.x;
+        const uint32_t idx = rec.y >> 4;
+        uint32_t bits = rec.y & 15u;
+        const int list = g->list;
+        const int64_t row = g->beg + idx;
+        const uint8_t* code = p.codes + row * M;
+        const float* crow = p.cent + static_cast<int64_t>(list) * p.d;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            const int pair = g->pair[b], q = g->query[b];
+            const uint32_t db = __float_as_uint(st_exact<M>(code, p.xq + static_cast<int64_t>(q) * p.d, crow, p.pq, p.dsub));
+            nev++;
+            const uint64_t key = make_key(db, __ldg(st.prefix + pair) + idx);
+            if (key <= __ldg(st.qkey + q)) {
+                const unsigned int s = atomicAdd(&st.qcnt[q], 1u);
+                if (s < static_cast<unsigned int>(st.capq)) {
+                    st.slab[static_cast<size_t>(q) * st.capq + s] = key;
+                } else if (s == static_cast<unsigned int>(st.capq)) {
+                    st.qflag[q] = 1;
+                    atomicOr(&st.ctr->overflow, 4);
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) nev += __shfl_xor_sync(0xffffffffu, nev, o);
+    if ((tid & 31) == 0 && nev) atomicAdd(&st.ctr->evals, nev);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// C: per-query selection + id lookup
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+st_select_kernel(const StParams st, const int32_t* __restrict__ probe, const int64_t* __restrict__ offsets, int nprobe,
+                 int k) {
+    if (threadIdx.x == 0) {
+        const unsigned int c = st.qcnt[blockIdx.x];
+        atomicAdd(&st.ctr->kept, static_cast<unsigned long long>(c));
+        atomicMax(&st.ctr->maxkept, c);
+        if (st.qflag[blockIdx.x] != 0) atomicAdd(&st.ctr->nflag, 1u);
+    }
+    // the fallback launches answer: everything after a batch-wide overflow, this query after a slab overflow
+    if ((*reinterpret_cast<const volatile int*>(&st.ctr->overflow) & 3) != 0 || st.qflag[blockIdx.x] != 0) return;
+    extern __shared__ __align__(16) unsigned char smem_sel[];
+    TopK tk;
+    tk.bind(smem_sel, k, kStSelCap);
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    if (tid == 0) tk.reset(kInfBits);
+    __syncthreads();
+    const unsigned int n = min(st.qcnt[q], static_cast<unsigned int>(st.capq));
+    const uint64_t* keys = st.slab + static_cast<size_t>(q) * st.capq;
+    uint32_t thr = kInfBits;
+    for (unsigned int base = 0; base < n; base += kThreads * 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned int i = base + u * kThreads + tid;
+            uint64_t key = kPadKey;
+            if (i < n) key = keys[i];
+            tk.push(i < n && static_cast<uint32_t>(key >> 32) <= thr, key);
+        }
+        tk.sync_and_flush_if_over<kThreads>(kStSelCap - kThreads * 4, kInfBits);
+        thr = tk.threshold();
+    }
+    __syncthreads();
+    tk.flush<kThreads>(kInfBits);
+    const int nb = tk.count();
+    const uint64_t* s = tk.sorted();
+    const uint32_t* pre = st.prefix + q * nprobe;
+    for (int i = tid; i < k; i += kThreads) {
+        float dv = FLT_MAX;
+        int64_t id = -1;
+        if (i < nb) {
+            const uint32_t tag = static_cast<uint32_t>(s[i] & 0xffffffffu);
+            int lo = 0, hi = nprobe - 1;      // last rank whose first scan position is <= tag
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (pre[mid] <= tag) lo = mid;
+                else hi = mid - 1;
+            }
+            const int64_t pos = offsets[probe[q * nprobe + lo]] + (tag - pre[lo]);
+            id = st.ids ? st.ids[pos] : pos;
+            dv = __uint_as_float(static_cast<uint32_t>(s[i] >> 32));
+        }
+        st.D[q * k + i] = dv;
+        st.I[q * k + i] = id;
+    }
+}
+
+}  // namespace b200

@@ -22,6 +22,8 @@ struct PairStats {
     int work_counter;                // dynamic scheduler of scan_pairs_kernel
     int ngroups;                     // number of same-list pair groups (scan_duo.cuh / scan_quad.cuh), sum over lists
                                      // of ceil(cnt / group size)
+    int work_counter2;               // scheduler of a second pass over the same work items (scan_stream.cuh fallback)
+    int pad_;
 };
 
 struct ScanParams {

@@ -17,12 +17,19 @@ import _util
 pytestmark = pytest.mark.gpu
 
 
-def _load(a, variant="qlut", stats=False):
+def _load(a, variant="qlut", stats=False, stream=1, env=None):
+    """stream = 1: the streaming pipeline (csrc/scan_stream.cuh: bootstrap thresholds, filter, exact evaluation, select,
+    with the in-kernel path as its overflow fallback); stream = 0: the in-kernel top-k path (scan_qlut_kernel) alone."""
     import b200ivfpq as faiss
-    old = {k: os.environ.get(k) for k in ("B200_IVFPQ_SCAN", "B200_IVFPQ_QL_STATS")}
+    names = ("B200_IVFPQ_SCAN", "B200_IVFPQ_QL_STATS", "B200_IVFPQ_STREAM", "B200_IVFPQ_STREAM_MINREC",
+             "B200_IVFPQ_STREAM_RATE")
+    old = {k: os.environ.get(k) for k in names}
     os.environ["B200_IVFPQ_SCAN"] = variant
+    os.environ["B200_IVFPQ_STREAM"] = str(stream)
     if stats:
         os.environ["B200_IVFPQ_QL_STATS"] = "1"
+    for k_, v_ in (env or {}).items():
+        os.environ[k_] = v_
     try:
         index = faiss.IndexIVFPQ(faiss.IndexFlatL2(a["d"]), a["d"], a["nlist"], a["M"], 8)
         index.set_codebooks(a["coarse"], a["pq"])
@@ -38,12 +45,13 @@ def _load(a, variant="qlut", stats=False):
 
 def _check(oracle, a, xq, nprobe, k, what, repeats=2):
     Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
-    index = _load(a)
-    index.nprobe = nprobe
-    for _ in range(repeats):      # the grouping of queries depends on atomics' order; the results must not
-        D, I = index.search(xq, k)
-        _util.assert_bit_equal(D, Dr, f"D ({what})")
-        _util.assert_bit_equal(I, Ir, f"I ({what})")
+    for stream in (1, 0):
+        index = _load(a, stream=stream)
+        index.nprobe = nprobe
+        for _ in range(repeats):      # the grouping of queries depends on atomics' order; the results must not
+            D, I = index.search(xq, k)
+            _util.assert_bit_equal(D, Dr, f"D ({what}, stream={stream})")
+            _util.assert_bit_equal(I, Ir, f"I ({what}, stream={stream})")
     return index
 
 
@@ -146,7 +154,7 @@ def test_qlut_filter_actually_filters(oracle):
     """The exact path alone would also pass the parity tests: make sure the filter does the work."""
     import b200ivfpq as faiss
     a, xq = _scaled(oracle, 5, 128, 16, 16, 120000, 256, 1.0, 0.0)
-    index = _load(a, stats=True)
+    index = _load(a, stats=True, stream=0)
     index.nprobe = 8
     D, I = index.search(xq, 10)
     Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 8, 10)
@@ -158,6 +166,37 @@ def test_qlut_filter_actually_filters(oracle):
     codes = index.last_scan_stats()["codes"]
     assert out[2] > 0 and out[1] > 0
     assert out[1] < 0.1 * codes, f"{out[1]} exact evaluations for {codes} (query, code) pairs: the filter is not filtering"
+
+
+def test_stream_overflow_falls_back(oracle):
+    """A survivor buffer far too small for the batch: the device raises the overflow flag and the guarded launches
+    (in-kernel path + merge) answer; the results are the oracle's either way."""
+    import b200ivfpq as faiss
+    a, xq = _scaled(oracle, 11, 128, 16, 16, 60000, 128, 1.0, 0.0)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 8, 10)
+    for minrec, expect_overflow in (("64", True), ("4194304", False)):
+        index = _load(a, stats=True, env={"B200_IVFPQ_STREAM_MINREC": minrec, "B200_IVFPQ_STREAM_RATE": "1e-6"})
+        index.nprobe = 8
+        D, I = index.search(xq, 10)
+        _util.assert_bit_equal(D, Dr, f"D (minrec {minrec})")
+        _util.assert_bit_equal(I, Ir, f"I (minrec {minrec})")
+        st = index.filter_stats(reset=True)
+        assert (st["work_items"] < 0) == expect_overflow, st
+
+
+def test_stream_survivors_are_few(oracle):
+    """With bootstrap thresholds the filter passes well under 2 % of the (query, code) pairs on clustered data."""
+    a, xq = _scaled(oracle, 5, 128, 16, 16, 120000, 256, 1.0, 0.0)
+    index = _load(a, stats=True)
+    index.nprobe = 8
+    D, I = index.search(xq, 10)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 8, 10)
+    _util.assert_bit_equal(D, Dr, "D")
+    _util.assert_bit_equal(I, Ir, "I")
+    st = index.filter_stats(reset=True)
+    codes = index.last_scan_stats()["codes"]
+    assert st["work_items"] >= 0, "unexpected overflow"
+    assert 0 < st["exact_evaluations"] < 0.02 * codes, (st, codes)
 
 
 def test_qlut_lists_replaced(oracle):
