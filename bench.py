@@ -166,21 +166,71 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU algorithm (oracle port) on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def synth_index_cpu(cfg, seed=1234, scale_nb=None):
-    """Same-shape synthetic index built on the CPU only: random codebooks, uniformly random codes, multinomial list
-    sizes.  CPU search cost depends on the shapes (nlist, M, list sizes, nprobe, k), not on the code values."""
+REF_SHRINK = {"c1": 1, "c2": 8, "c3": 64, "c4": 8, "c5": 8}   # the CPU arm's index is nb / shrink vectors in nlist / shrink lists
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads(oracle):
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: the CPU arm must not inherit that."""
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    oracle.C.set_num_threads(n)
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return oracle.C.num_threads()
+
+
+def build_index_cpu(cfg, shrink, args):
+    """The GPU arm's data (same ClusteredGenerator, same seeds, same 12-dimensional blobs), built with host code only
+    (torch CPU GEMMs + numpy; none of this repo's kernels): nb / shrink vectors in nlist / shrink lists, so that a list is
+    as long as in the full-size index and a query scans the same number of codes and builds the same number of look-up
+    tables with the SAME nprobe -- the per-query work of the path -- while the build stays within a minute of host time.
+    Only the coarse stage is smaller (nlist / shrink centroids)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "chameleon-rag-acceleration_b200"))
+    from b200ivfpq.datasets import SEED_BASE, SEED_QUERY, SEED_TRAIN, ClusteredGenerator
+    from b200ivfpq.kmeans import _assign, kmeans, kmeans_subspaces
+
     nb, d, nlist, M, nprobe, k, nq = cfg
-    if scale_nb:
-        nb = scale_nb
-    rng = np.random.default_rng(seed)
-    coarse = rng.random((nlist, d), dtype=np.float32)
-    pq = (rng.standard_normal((M, 256, d // M)) * 0.1).astype(np.float32)
-    sizes = rng.multinomial(nb, np.full(nlist, 1.0 / nlist))
-    offsets = np.zeros(nlist + 1, np.int64)
-    offsets[1:] = np.cumsum(sizes)
-    codes = rng.integers(0, 256, size=(nb, M), dtype=np.uint8)
-    ids = np.arange(nb, dtype=np.int64)
-    return coarse, pq, offsets, codes, ids
+    nb_r, nlist_r = max(nb // shrink, 1), max(nlist // shrink, nprobe)
+    cpu = torch.device("cpu")
+    gen = ClusteredGenerator(d, ncentres=max(16, nlist_r // 2), sigma=args.sigma, device=cpu, seed=7,
+                             latent_dim=args.latent_dim, sigma_iso=args.sigma_iso)
+    ntrain = min(nb_r, max(64 * nlist_r, 65536))
+    xt = torch.cat([gen.chunk(SEED_TRAIN, i, min(1 << 18, ntrain - (i << 18))) for i in range((ntrain + (1 << 18) - 1) >> 18)])
+    coarse = kmeans(xt, nlist_r, niter=8, seed=1234)
+    lab, _ = _assign(xt[:65536], coarse)
+    pq = kmeans_subspaces(xt[:65536] - coarse[lab], M, 256, niter=8, seed=4321)
+    del xt
+    dsub = d // M
+    list_no = np.empty(nb_r, np.int32)
+    codes = np.empty((nb_r, M), np.uint8)
+    chunk = 1 << 18
+    pn = (pq * pq).sum(2)                                              # (M, 256)
+    for i0 in range(0, nb_r, chunk):
+        x = gen.chunk(SEED_BASE, i0 // chunk, min(chunk, nb_r - i0))
+        l, _ = _assign(x, coarse)
+        r = (x - coarse[l]).reshape(-1, M, dsub).permute(1, 0, 2)       # (M, n, dsub)
+        dist = torch.baddbmm(pn.unsqueeze(1), r, pq.transpose(1, 2), alpha=-2.0)
+        codes[i0:i0 + x.shape[0]] = dist.argmin(2).t().to(torch.uint8).numpy()
+        list_no[i0:i0 + x.shape[0]] = l.numpy()
+    order = np.argsort(list_no, kind="stable")
+    offsets = np.zeros(nlist_r + 1, np.int64)
+    offsets[1:] = np.cumsum(np.bincount(list_no, minlength=nlist_r))
+    xq = gen.chunk(SEED_QUERY, 0, nq).numpy()
+    arrays = (np.ascontiguousarray(coarse.numpy()), np.ascontiguousarray(pq.numpy()), offsets,
+              np.ascontiguousarray(codes[order]), order.astype(np.int64))
+    return arrays, np.ascontiguousarray(xq), nb_r, nlist_r
 
 
 def time_oracle(oracle, xq, arrays, nprobe, k, budget_s=15.0, max_q=None):
@@ -198,27 +248,42 @@ def time_oracle(oracle, xq, arrays, nprobe, k, budget_s=15.0, max_q=None):
     return n / dt, n, dt, D, I
 
 
+def bench_config(cfg, args):
+    """The `config` object of the JSON line: the workload and nothing run-dependent, identical in both arms."""
+    nb, d, nlist, M, nprobe, k, nq = cfg
+    return {"workload": workload_name(cfg, args), "nb": nb, "d": d, "index": f"IVF{nlist},PQ{M}x8", "nprobe": nprobe,
+            "k": k, "batch": nq}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import ivfpq_oracle as oracle
     oracle.build()
-    cfg = CONFIGS[args.config]
+    cores = use_all_host_threads(oracle)
+    cfg = apply_overrides(CONFIGS[args.config], args)
     nb, d, nlist, M, nprobe, k, nq = cfg
-    cores = oracle.C.num_threads()
-    log(f"[reference] building same-shape synthetic index on the CPU ({nb} codes) ...")
-    arrays = synth_index_cpu(cfg)
-    rng = np.random.default_rng(4321)
-    xq = rng.random((nq, d), dtype=np.float32)
-    # a step = a bounded sample of the 10k-query batch, sized from a pilot so that the run ends in minutes
-    npilot = min(32, nq)
+    shrink = REF_SHRINK[args.config] if not args.nb else max(1, nb // 12_500_000)
     t0 = time.perf_counter()
-    oracle.C.search(xq[:npilot], *arrays, nprobe, k)
+    log(f"[reference] {cores} host threads; building the clustered index on the CPU ({nb // shrink} vectors, "
+        f"IVF{max(nlist // shrink, nprobe)}) ...")
+    arrays, xq, nb_r, nlist_r = build_index_cpu(cfg, shrink, args)
+    log(f"[reference] built in {time.perf_counter() - t0:.1f} s")
+    # a step = the 10k-query batch, or the part of it that keeps the whole run within a few minutes
+    npilot = min(64, nq)
+    t0 = time.perf_counter()
+    D0, I0 = oracle.C.search(xq[:npilot], *arrays, nprobe, k)
     per_q = (time.perf_counter() - t0) / npilot
+    offsets = arrays[2]
     total = args.steps + args.warmup
-    nq_step = int(max(1, min(nq, (120.0 / max(total, 1)) / max(per_q, 1e-9))))
-    log(f"[reference] {per_q * 1e3:.2f} ms/query on {cores} threads -> {nq_step} queries per step")
+    nq_step = int(max(1, min(nq, (150.0 / max(total, 1)) / max(per_q, 1e-9))))
+    # scan bytes per query of this index (what the CPU arm streams per query), for comparison with the GPU arm's
+    pl = oracle.C.search(xq[:npilot], *arrays, nprobe, k, return_probes=True)[3]
+    sizes = np.diff(offsets)
+    scan_mb = float(sizes[np.maximum(pl, 0)].sum() * M / npilot / 1e6)
+    log(f"[reference] {per_q * 1e3:.2f} ms/query on {cores} threads -> {nq_step} queries per step; "
+        f"{scan_mb:.2f} MB of codes scanned per query")
     for _ in range(args.warmup):
         oracle.C.search(xq[:nq_step], *arrays, nprobe, k)
     times = []
@@ -228,19 +293,31 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
     qps = nq_step / (ms / 1e3)
-    sample = (f"{nq_step} of {nq} queries per step on a same-shape synthetic index (uniform random codes, "
-              f"multinomial list sizes); restated Faiss-CPU algorithm (oracle/ivfpq_oracle.c, OpenMP), "
-              f"not the Faiss binary")
+    sample = (f"{nq_step} of {nq} queries per step, {cores} OpenMP threads, same generator / seeds / nprobe / k as the GPU "
+              f"arm on a 1/{shrink}-size index ({nb_r} vectors, IVF{nlist_r}: lists as long as the full index's, "
+              f"{scan_mb:.2f} MB of codes and {nprobe} look-up tables per query; only the coarse stage is 1/{shrink}); "
+              f"restated Faiss-CPU algorithm (oracle/ivfpq_oracle.c, residual look-up tables built per probe, no "
+              f"precomputed-table shortcut), not the Faiss binary")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32/u8", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, args), "queries_per_step": nq_step},
+        "config": bench_config(cfg, args), "queries_per_step": nq_step, "scan_mbytes_per_query": scan_mb,
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
     return 0
+
+
+def apply_overrides(cfg, args):
+    if args.nb:
+        cfg = (args.nb,) + cfg[1:]
+    if args.nq:
+        cfg = cfg[:6] + (args.nq,)
+    if args.nprobe:
+        cfg = cfg[:4] + (args.nprobe,) + cfg[5:]
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -334,6 +411,83 @@ def build_index(cfg, rank, world, device, dist, args, layout=None):
     return index, xq[:nq].contiguous(), gt_i, {"train_s": t_train, "add_s": t_add}
 
 
+def compare_results(Dg, Ig, Dr, Ir):
+    """GPU result vs oracle: distance bits, ids, and ids up to the order inside runs of equal distance (what a merge of
+    shards may legitimately change: BASELINE exempts ties)."""
+    bits_equal = bool(np.array_equal(Dg.view(np.uint32), Dr.view(np.uint32)))
+    ids_equal = bool(np.array_equal(Ig, Ir))
+    ties_ok, bad = True, 0
+    if bits_equal and not ids_equal:
+        k = Dg.shape[1]
+        for q in np.nonzero((Ig != Ir).any(1))[0]:
+            d = Dr[q].view(np.uint32)
+            i = 0
+            while i < k:
+                j = i
+                while j + 1 < k and d[j + 1] == d[i]:
+                    j += 1
+                if sorted(Ig[q, i:j + 1].tolist()) != sorted(Ir[q, i:j + 1].tolist()) and j != k - 1:
+                    ties_ok = False
+                    bad += 1
+                    break
+                i = j + 1
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = float(np.nanmax(np.abs(Dg - Dr) / np.maximum(np.abs(Dr), 1e-30))) if Dg.size else 0.0
+    return {"distances_bit_exact": bits_equal, "ids_identical": ids_equal,
+            "ids_identical_modulo_ties": bool(bits_equal and ties_ok), "queries_differing_outside_ties": int(bad),
+            "max_rel_dist_err": rel}
+
+
+def gather_probed_lists(index, xq_s, nprobe, rank, world, dist, device):
+    """The oracle's view of the WHOLE (unsharded) index restricted to the lists the sample queries probe: every rank
+    sends the entries of those lists to rank 0, which concatenates them list by list in rank order (= the order a single
+    index holding shard 0's entries first would have).  Unprobed lists are left empty, which no sample query can see."""
+    import torch
+    nlist = index.nlist
+    _, probes = index.quantizer.search(xq_s, min(nprobe, nlist))      # bit-identical to the oracle's coarse stage (tested)
+    need = torch.zeros(nlist, dtype=torch.bool, device=device)
+    need[probes.flatten().clamp(min=0)] = True
+    index._finalize_lists()
+    off = torch.from_numpy(index._offsets).to(device)
+    lists = torch.nonzero(need).flatten()
+    lens = (off[1:] - off[:-1])[lists]
+    tot = int(lens.sum())
+    cum = torch.cumsum(lens, 0) - lens
+    rows = torch.repeat_interleave(off[lists], lens) + (torch.arange(tot, device=device) - torch.repeat_interleave(cum, lens))
+    codes, ids = index._codes[rows].contiguous(), index._ids[rows].contiguous()
+    list_no = torch.repeat_interleave(lists, lens)
+    del rows
+    if world > 1:
+        if rank == 0:
+            parts = [(list_no, codes, ids)]
+            for r in range(1, world):
+                n = torch.zeros(1, dtype=torch.int64, device=device)
+                dist.recv(n, src=r)
+                ln = torch.empty(int(n), dtype=torch.int64, device=device)
+                cd = torch.empty((int(n), codes.shape[1]), dtype=torch.uint8, device=device)
+                ii = torch.empty(int(n), dtype=torch.int64, device=device)
+                dist.recv(ln, src=r)
+                dist.recv(cd, src=r)
+                dist.recv(ii, src=r)
+                parts.append((ln, cd, ii))
+            list_no = torch.cat([p[0] for p in parts])
+            codes = torch.cat([p[1] for p in parts])
+            ids = torch.cat([p[2] for p in parts])
+            del parts
+        else:
+            dist.send(torch.tensor([list_no.shape[0]], dtype=torch.int64, device=device), dst=0)
+            dist.send(list_no.contiguous(), dst=0)
+            dist.send(codes, dst=0)
+            dist.send(ids, dst=0)
+            return None
+    _, order = torch.sort(list_no, stable=True)
+    counts = torch.bincount(list_no, minlength=nlist).cpu().numpy()
+    offsets = np.zeros(nlist + 1, np.int64)
+    offsets[1:] = np.cumsum(counts)
+    return (index.quantizer.xb_tensor().cpu().numpy(), index.pq.centroids_tensor().cpu().numpy(), offsets,
+            codes[order].cpu().numpy(), ids[order].cpu().numpy())
+
+
 def run_ours(args):
     import torch
 
@@ -353,13 +507,7 @@ def run_ours(args):
     import b200ivfpq as faiss
     from b200ivfpq.shards import DistributedIndexIVFPQ
 
-    cfg = CONFIGS[args.config]
-    if args.nb:
-        cfg = (args.nb,) + cfg[1:]
-    if args.nq:
-        cfg = cfg[:6] + (args.nq,)
-    if args.nprobe:
-        cfg = cfg[:4] + (args.nprobe,) + cfg[5:]
+    cfg = apply_overrides(CONFIGS[args.config], args)
     nb, d, nlist, M, nprobe, k, nq = cfg
     if rank == 0:
         log(f"[bench] {workload_name(cfg, args)} on {world} GPU(s)")
@@ -437,9 +585,11 @@ def run_ours(args):
     qps = nq / (ms_per_step / 1e3)
 
     # per-stage device times (CUDA events recorded by the library on the launching stream); a few extra steps
+    filter_ms = []
     for _ in range(min(args.steps, 5)):
         step_device()
         st = index.stage_ms()
+        filter_ms.append(index.filter_ms())
         scan_ms.append(st["scan"])
         for kk, v in st.items():
             stage_acc.setdefault(kk, []).append(v)
@@ -494,78 +644,100 @@ def run_ours(args):
     lat_p50 = float(np.median(lat))
     del q1
 
-    # ---- roofline of the dominant kernel (K2+K3+K4 scan) -----------------------------------------------
+    # ---- roofline of the dominant kernel --------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = stats["bytes"] / (scan_t / 1e3) / 1e9
-    traffic = None
+    filt = [v for v in filter_ms if v is not None]
+    if filt:
+        kern_name, kern_ms = "st_filter_kernel (integer lower-bound filter over the probed lists)", float(np.mean(filt))
+    else:
+        kern_name, kern_ms = "scan stage (table set-up + ADC scan + top-k)", scan_t
+    achieved = stats["bytes"] / (kern_ms / 1e3) / 1e9
+    # DRAM traffic of that kernel: one `ncu --set full` capture of the same command, kept under profiles/ with the
+    # kernel name, config and GPU count it belongs to (never reused for another kernel or shape)
+    traffic, traffic_src, pipe_pct = None, None, None
     tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
     if os.path.exists(tp):
         try:
-            tj = json.load(open(tp))
-            if tj.get("config") == args.config and tj.get("n_gpus", 1) == world:
-                traffic = tj.get("dram_bytes_per_launch")
+            for tj in json.load(open(tp)).get("captures", []):
+                if (tj.get("config") == args.config and tj.get("n_gpus", 1) == world and not args.nb and
+                        tj.get("kernel", "").split("<")[0] in kern_name):
+                    traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+                    pipe_pct = tj.get("l1_data_pipe_pct")
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": "scan (K2+K3+K4: LUT + ADC + top-k)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": stats["bytes"], "launch_ms": scan_t,
-                "note": "algorithmic bytes = sum over probed lists of list_size*M; codes of a list are re-read "
-                        "from L2 by the ~nq*nprobe/nlist queries that probe it, so DRAM traffic << algorithmic"}
+    dram_frac = (traffic / (kern_ms / 1e3) / 1e9 / peak) if traffic else None
+    hbm_bound = dram_frac is not None and dram_frac > 0.5
+    roofline = {"bound": "hbm" if hbm_bound else "l1/shared-memory data pipe (codes are served from L2: each probed list "
+                         "is scanned by the ~nq*nprobe/nlist queries that probe it; DRAM traffic << algorithmic bytes)",
+                "kernel": kern_name, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": stats["bytes"], "launch_ms": kern_ms,
+                "hbm_equivalent_frac": achieved / peak, "dram_frac": dram_frac, "l1_data_pipe_pct": pipe_pct,
+                "note": "achieved = algorithmic bytes (sum over probed lists of list_size*M) / kernel time: an equivalent "
+                        "streaming rate, it exceeds the DRAM rate by the L2 reuse factor and can exceed 1.0 of the copy "
+                        "peak; dram_frac = measured DRAM bytes (ncu capture) / kernel time / peak; l1_data_pipe_pct = "
+                        "ncu l1tex__data_pipe_lsu_wavefronts, the pipe that bounds the kernel"}
 
-    # ---- CPU baseline beside it (rank 0, N = 1): the oracle on the SAME index and queries --------------
+    # ---- CPU baseline + parity (any N): the oracle on the SAME index and queries -----------------------
     cpu_baseline, parity = None, None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import ivfpq_oracle as oracle
-        oracle.build()
-        a = index.to_arrays()
-        arrays = (a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"])
-        cqps, n_used, dt, Dr, Ir = time_oracle(oracle, xq_np, arrays, nprobe, k, budget_s=args.cpu_budget_s)
-        Dg, Ig = D[:n_used].cpu().numpy(), I[:n_used].cpu().numpy()
-        parity = {"queries": int(n_used),
-                  "distances_bit_exact": bool(np.array_equal(Dg.view(np.uint32), Dr.view(np.uint32))),
-                  "ids_identical": bool(np.array_equal(Ig, Ir)),
-                  "max_rel_dist_err": float(np.max(np.abs(Dg - Dr) / np.maximum(np.abs(Dr), 1e-30))),
-                  "oracle": "CPU restatement (oracle/), itself pinned against the reference's own code run as a C "
-                            "simulation (oracle/_ref: hnswlib cell selection + accelerator kernel); not the Faiss binary"}
-        if gt.shape[0]:
-            ng = min(gt.shape[0], n_used)
-            gc = gt[:ng].cpu().numpy()
-            parity["recall_at_10_oracle"] = float(
-                sum(np.intersect1d(x_, y_).shape[0] for x_, y_ in zip(Ir[:ng, :10], gc)) / gc.size)
-            parity["recall_at_10_ours_same_queries"] = float(
-                sum(np.intersect1d(x_, y_).shape[0] for x_, y_ in zip(Ig[:ng, :10], gc)) / gc.size)
-        cpu_baseline = {"value": cqps, "unit": "queries/s", "cores": oracle.C.num_threads(), "kind": "port",
-                        "sample": f"first {n_used} of {nq} queries, same index and queries as the GPU run, "
-                                  f"{dt:.1f} s; restated Faiss-CPU algorithm (oracle, OpenMP), not the Faiss binary"}
-        log(f"[bench] cpu baseline {cqps:.1f} q/s on {cpu_baseline['cores']} threads; parity {parity}")
+    # layouts whose shards are disjoint parts of ONE index (the default by-vector split, whole lists per GPU) are
+    # gathered from all ranks; a replicated index is checked on rank 0's copy; mixed R x S layouts are not checked
+    gather_world = world if (R == 1 or world == 1) else 1 if R == world else 0
+    if not args.no_cpu_baseline and gather_world and (gather_world > 1 or rank == 0):
+        ns = min(nq, args.parity_queries or (256 if nb * M > 8e9 else nq))
+        arrays = gather_probed_lists(index, xq[:ns], nprobe, rank, gather_world, dist, device)
+        if rank == 0:
+            from oracle import ivfpq_oracle as oracle
+            oracle.build()
+            cores = use_all_host_threads(oracle)
+            cqps, n_used, dt, Dr, Ir = time_oracle(oracle, xq_np[:ns], arrays, nprobe, k, budget_s=args.cpu_budget_s)
+            Dg, Ig = D[:n_used].cpu().numpy(), I[:n_used].cpu().numpy()
+            parity = {"queries": int(n_used), **compare_results(Dg, Ig, Dr, Ir),
+                      "against": f"oracle on the unsharded index (entries of all {world} shards, lists probed by the sample)",
+                      "oracle": "CPU restatement (oracle/), itself pinned against the reference's own code run as a C "
+                                "simulation (oracle/_ref: hnswlib cell selection + accelerator kernel); not the Faiss binary"}
+            if gt.shape[0]:
+                ng = min(gt.shape[0], n_used)
+                gc = gt[:ng].cpu().numpy()
+                parity["recall_at_10_oracle"] = float(
+                    sum(np.intersect1d(x_, y_).shape[0] for x_, y_ in zip(Ir[:ng, :10], gc)) / gc.size)
+                parity["recall_at_10_ours_same_queries"] = float(
+                    sum(np.intersect1d(x_, y_).shape[0] for x_, y_ in zip(Ig[:ng, :10], gc)) / gc.size)
+            cpu_baseline = {"value": cqps, "unit": "queries/s", "cores": cores, "kind": "port",
+                            "sample": f"first {n_used} of {nq} queries, same index (all {world} shard(s)) and queries as the "
+                                      f"GPU run, {dt:.1f} s; restated Faiss-CPU algorithm (oracle, OpenMP; residual look-up "
+                                      f"tables per probe, no precomputed-table shortcut), not the Faiss binary"}
+            log(f"[bench] cpu baseline {cqps:.1f} q/s on {cores} threads; parity {parity}")
+            del arrays
 
     if rank == 0:
+        sharding = (f"by list (NOT the reference's split): list l on GPU l % {world}, probes of other GPUs' lists masked"
+                    if args.shard_mode == "list" and world > 1 else
+                    f"replicated (Faiss IndexReplicas, NOT the sharded config): full index on each of "
+                    f"{world} GPUs, batch sliced by query, results all-gathered"
+                    if R == world and world > 1 else
+                    f"{R} replicas (batch sliced by query) x {world // R} shards by vector (the reference's "
+                    f"-R {R}); NOT the all-GPU sharded config" if R > 1 else
+                    f"by vector: 2M-vector chunks round-robin over {world} GPU(s)")
+        shard_merge = ("none" if world == 1 else
+                       "none: NCCL all-gather of the per-slice results" if R == world else
+                       "K5 reads every shard's top-k in place over NVLink (symmetric memory)"
+                       if getattr(searcher, "peer_merge", False) else
+                       "NCCL all-gather + K5" + (f" (peer memory unavailable: {searcher.peer_merge_error})"
+                                                 if getattr(searcher, "peer_merge_error", None) else ""))
         line = {
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32/u8", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, args), "sharding": (f"by list (NOT the reference's split): list l on GPU l % {world}, probes of other GPUs' lists masked"
-                                    if args.shard_mode == "list" and world > 1 else
-                                    f"replicated (Faiss IndexReplicas, NOT the sharded config): full index on each of "
-                                    f"{world} GPUs, batch sliced by query, results all-gathered"
-                                    if R == world and world > 1 else
-                                    f"{R} replicas (batch sliced by query) x {world // R} shards by vector (the reference's "
-                                    f"-R {R}); NOT the all-GPU sharded config" if R > 1 else
-                                    f"by vector: 2M-vector chunks round-robin over {world} GPU(s)"),
-                       "shard_merge": ("none" if world == 1 else
-                                       "none: NCCL all-gather of the per-slice results" if R == world else
-                                       "K5 reads every shard's top-k in place over NVLink (symmetric memory)"
-                                       if getattr(searcher, "peer_merge", False) else
-                                       "NCCL all-gather + K5" + (f" (peer memory unavailable: {searcher.peer_merge_error})"
-                                                                 if getattr(searcher, "peer_merge_error", None) else "")),
-                       "l2_policy": "inputs larger than L2 (codes %.0f MB per GPU vs 126 MB L2)" %
-                                    (index.ntotal * M / 1e6),
-                       "scan_kernel": os.environ.get("B200_IVFPQ_SCAN", "auto"), "ntotal_per_gpu": index.ntotal,
-                       "build": build_info},
+            "config": bench_config(cfg, args),
+            "details": {"sharding": sharding, "shard_merge": shard_merge,
+                        "l2_policy": "inputs larger than L2 (codes %.0f MB per GPU vs 126 MB L2)" % (index.ntotal * M / 1e6),
+                        "scan_kernel": os.environ.get("B200_IVFPQ_SCAN", "auto"), "ntotal_per_gpu": index.ntotal,
+                        "build": build_info},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_qps, "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * d * 4,
                     "d2h_bytes_per_step": nq * k * 12},
@@ -598,6 +770,9 @@ def parse_args(argv=None):
     ap.add_argument("--gt-queries", type=int, default=1000)
     ap.add_argument("--kmeans-iters", type=int, default=25, help="Lloyd iterations for index.train (Faiss default 25)")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--parity-queries", type=int, default=0,
+                    help="queries (from the start of the batch) checked against the oracle and timed on the CPU; 0 = the whole "
+                         "batch, or 256 when the index is too large to copy to the host (C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", type=int, default=1,
                     help="N > 1: R replica groups of N/R vector shards each, the batch sliced by query between the "

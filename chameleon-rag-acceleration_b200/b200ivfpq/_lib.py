@@ -37,6 +37,7 @@ SYMBOLS = [
     ("b200_ivfpq_get_stage_ms", _I, [_P, _P]),
     ("b200_ivfpq_get_last_scan_stats", _I, [_P, _P, _P]),
     ("b200_ivfpq_get_filter_stats", _I, [_P, _P, _I]),
+    ("b200_ivfpq_get_filter_ms", _I, [_P, _P]),
 ]
 
 

@@ -516,6 +516,14 @@ class IndexIVFPQ:
         _lib.check(h.lib.b200_ivfpq_get_last_scan_stats(h.h, ctypes.byref(b), ctypes.byref(c)))
         return {"bytes": int(b.value), "codes": int(c.value)}
 
+    def filter_ms(self):
+        """Device time of the streaming filter kernel in the last timed search, or None if it did not run."""
+        h = self._ensure_handle()
+        out = ctypes.c_float()
+        if h.lib.b200_ivfpq_get_filter_ms(h.h, ctypes.byref(out)) != 0:
+            return None
+        return float(out.value)
+
     def filter_stats(self, reset: bool = True):
         """Counters of the per-query-table filter scan since the last reset (zeros unless the handle was created with
         B200_IVFPQ_QL_STATS=1): survivor entries, exact evaluations, work items."""

@@ -130,10 +130,11 @@ struct b200_ivfpq_index {
     int kpad = 0;
     // instrumentation
     bool timing = false;
-    std::vector<std::array<cudaEvent_t, 6>> evs;   // one event set per query chunk of the last search
+    std::vector<std::array<cudaEvent_t, 8>> evs;   // one event set per query chunk of the last search ([6], [7]: filter kernel)
     cudaEvent_t* ev = nullptr;                     // event set of the chunk being enqueued
     int timed_chunks = 0;
     bool stage_valid = false;
+    bool filter_timed = false;   // the last timed search ran the streaming filter kernel (events [6], [7])
     cudaStream_t last_stream = nullptr;
     // small-batch latency path: the whole host-buffer search (H2D, kernels, D2H) replayed as a CUDA graph
     struct GraphEntry {
@@ -155,7 +156,7 @@ namespace {
 
 int ensure_events(b200_ivfpq_index* h, size_t nchunks) {
     while (h->evs.size() < nchunks) {
-        std::array<cudaEvent_t, 6> set{};
+        std::array<cudaEvent_t, 8> set{};
         for (auto& e : set) CUDA_TRY(cudaEventCreate(&e));
         h->evs.push_back(set);
     }
@@ -395,6 +396,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     const int sv = legacy ? 0 : h->scan_variant;
     const bool timing = h->timing;
     h->stage_valid = false;
+    h->filter_timed = false;
     h->timed_chunks = 0;
     h->last_stream = st;
 
@@ -621,7 +623,9 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             qp.qflag = nullptr;
             if (st_ctas) {
                 // streaming pipeline: thresholds -> filter -> exact evaluation -> select; D / I are final after it ...
-                if (st_launch(sp, qp, sb, nqc, h->ids, d_D + q0 * k, d_I + q0 * k, st_ctas, h->num_sms, st))
+                if (tm) h->filter_timed = true;
+                if (st_launch(sp, qp, sb, nqc, h->ids, d_D + q0 * k, d_I + q0 * k, st_ctas, h->num_sms, st,
+                              tm ? h->ev[6] : nullptr, tm ? h->ev[7] : nullptr))
                     return fail(B200_IVFPQ_ECUDA, "streaming scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 g_launches.fetch_add(4);
                 // ... unless a buffer overflowed: then the guarded launches below recompute the batch
@@ -1079,6 +1083,21 @@ int b200_ivfpq_get_stage_ms(b200_ivfpq_t h, float* h_ms5) {
             CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
             h_ms5[i] += ms;
         }
+    }
+    return 0;
+}
+
+int b200_ivfpq_get_filter_ms(b200_ivfpq_t h, float* h_ms) {
+    if (!h || !h_ms) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    if (!h->stage_valid || h->timed_chunks == 0 || !h->filter_timed)
+        return fail(B200_IVFPQ_ESTATE, "no timed search through the streaming filter kernel recorded");
+    *h_ms = 0.0f;
+    for (int c = 0; c < h->timed_chunks; c++) {
+        auto& ev = h->evs[c];
+        CUDA_TRY(cudaEventSynchronize(ev[7]));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev[6], ev[7]));
+        *h_ms += ms;
     }
     return 0;
 }

@@ -155,7 +155,7 @@ int st_filter_grid_t(int64_t npairs, int num_sms) {
 
 template <int M>
 int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
-                cudaStream_t st) {
+                cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     const size_t bsm = st_boot_smem(sp.d, M, sp.nprobe, sp.k);
     if (bsm > 48 * 1024 &&
         cudaFuncSetAttribute(st_boot_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm) != cudaSuccess)
@@ -165,8 +165,10 @@ int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, i
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
     const size_t fsm = st_filter_smem<M>();
     if (cudaFuncSetAttribute(st_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
+    if (ev0 && cudaEventRecord(ev0, st) != cudaSuccess) return -1;
     st_filter_kernel<M><<<(unsigned)filter_grid, QlCfg<M>::kT, fsm, st>>>(sp, ql, stp);
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
+    if (ev1 && cudaEventRecord(ev1, st) != cudaSuccess) return -1;
     st_eval_kernel<M><<<(unsigned)(8 * num_sms), 256, 0, st>>>(sp, stp);
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
     const size_t ssm = TopK::smem_bytes(sp.k, kStSelCap);
@@ -189,7 +191,7 @@ int st_filter_grid(int M, int64_t npairs, int num_sms) {
 }
 
 int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,
-              int64_t* I, int filter_grid, int num_sms, cudaStream_t st) {
+              int64_t* I, int filter_grid, int num_sms, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     QlParams ql;
     ql.snorm = qp.snorm;
     ql.sbmin = qp.sbmin;
@@ -218,9 +220,9 @@ int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers&
     stp.I = I;
     if (cudaMemsetAsync(sb.ctr, 0, kStCtrBytes, st) != cudaSuccess) return -1;
     switch (sp.M) {
-        case 16: return st_launch_t<16>(sp, ql, stp, nq, filter_grid, num_sms, st);
-        case 32: return st_launch_t<32>(sp, ql, stp, nq, filter_grid, num_sms, st);
-        case 64: return st_launch_t<64>(sp, ql, stp, nq, filter_grid, num_sms, st);
+        case 16: return st_launch_t<16>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
+        case 32: return st_launch_t<32>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
+        case 64: return st_launch_t<64>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
         default: return -1;
     }
 }

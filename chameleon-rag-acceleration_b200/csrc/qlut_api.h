@@ -66,8 +66,9 @@ constexpr size_t kStCtrBytes = 48;
 constexpr int kStChunkRecords = 64;
 int st_filter_grid(int M, int64_t npairs, int num_sms);        // 0: does not fit
 // enqueues the four kernels; the overflow flag (an int, != 0 after an overflow) lives at st_overflow_flag(ctr)
+// ev0 / ev1 (optional): recorded right before / after the filter kernel
 int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,
-              int64_t* I, int filter_grid, int num_sms, cudaStream_t st);
+              int64_t* I, int filter_grid, int num_sms, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 const int* st_overflow_flag(const void* ctr);
 
 }  // namespace b200

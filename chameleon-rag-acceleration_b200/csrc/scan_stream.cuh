@@ -71,7 +71,7 @@ __host__ __device__ inline int st_boot_nsel(int k) {
 }
 __host__ __device__ inline size_t st_boot_smem(int d, int M, int nprobe, int k) {
     // query | the query's table | list sizes | prefix | list ids | TopK
-    return sizeof(float) * ((d + 3) & ~3) + sizeof(uint16_t) * 256 * M + 3 * sizeof(uint32_t) * nprobe +
+    return sizeof(float) * ((d + 3) & ~3) + sizeof(uint16_t) * 256 * (M + 2) + 3 * sizeof(uint32_t) * nprobe +
            TopK::smem_bytes(st_boot_nsel(k), kStSelCap) + 64;
 }
 
@@ -122,8 +122,11 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
     extern __shared__ __align__(16) unsigned char smem_boot[];
     const int dpad = (d + 3) & ~3;
     float* qv = reinterpret_cast<float*>(smem_boot);
-    uint16_t* s_lut = reinterpret_cast<uint16_t*>(qv + dpad);                 // [256][M] the query's table
-    uint32_t* s_sz = reinterpret_cast<uint32_t*>(s_lut + 256 * M);
+    // the query's table, rows padded to M + 2 entries: an odd number of 32-bit words, so that the gathers of a warp
+    // (same m, 32 different code values) spread over the banks
+    constexpr int kRow = M + 2;
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(qv + dpad);                 // [256][M + 2]
+    uint32_t* s_sz = reinterpret_cast<uint32_t*>(s_lut + 256 * kRow);
     uint32_t* s_pre = s_sz + nprobe;
     int32_t* s_list = reinterpret_cast<int32_t*>(s_pre + nprobe);
     const int nsel = st_boot_nsel(k);
@@ -135,9 +138,9 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
     const int64_t q = blockIdx.x;
     for (int j = tid; j < d; j += kStBootThreads) qv[j] = xq[q * d + j];
     {
-        const uint4* src = reinterpret_cast<const uint4*>(ql.qlut + q * 256 * M);
-        uint4* dst = reinterpret_cast<uint4*>(s_lut);
-        for (int i = tid; i < 256 * M / 8; i += kStBootThreads) dst[i] = __ldg(src + i);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(ql.qlut + q * 256 * M);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_lut);
+        for (int i = tid; i < 256 * M / 2; i += kStBootThreads) dst[(i / (M / 2)) * (kRow / 2) + (i % (M / 2))] = __ldg(src + i);
     }
     for (int r = tid; r < nprobe; r += kStBootThreads) {
         const int l = probe[q * nprobe + r];
@@ -192,8 +195,9 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
     const uint32_t ncand = static_cast<uint32_t>(s_total < kStBootCodes ? s_total : kStBootCodes);
     const float sq = ql.qscale[q], aq = ql.qamin[q];
     const float inv = sq > 0.0f ? 1.0f / sq : 0.0f;
-    constexpr int kPer = kStBootCodes / kStBootThreads;   // 8 candidates per thread, their loads in flight together
-    constexpr int kBatch = M == 16 ? 8 : M == 32 ? 4 : 2;
+    constexpr int kPer = kStBootCodes / kStBootThreads;   // 8 candidates per thread
+    constexpr int kBatch = 2;   // small batches: after the first fold most candidates fail the comparison with bthr
+    uint32_t bthr = kInfBits;
 #pragma unroll 1
     for (int i0 = 0; i0 < kPer; i0 += kBatch) {
         uint4 cv[kBatch][M / 16];
@@ -225,13 +229,16 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
                 const uint32_t w[4] = {cv[i][h].x, cv[i][h].y, cv[i][h].z, cv[i][h].w};
 #pragma unroll
                 for (int mm = 0; mm < 16; mm++)
-                    u += s_lut[((w[mm >> 2] >> (8 * (mm & 3))) & 255u) * M + 16 * h + mm];
+                    u += s_lut[((w[mm >> 2] >> (8 * (mm & 3))) & 255u) * kRow + 16 * h + mm];
             }
             const float est = add[i] + static_cast<float>(u) * inv;
             uint32_t bits = __float_as_uint(fmaxf(est, 0.0f));
             if (!(est == est)) bits = 0x7f7fffffu;                    // NaN estimates rank last
-            tk.push(pos < ncand, make_key(bits, pos));
+            tk.push(pos < ncand && bits <= bthr, make_key(bits, pos));
         }
+        // fold between the batches: the later candidates are compared with the nsel-th estimate found so far
+        tk.sync_and_flush_if_over<kStBootThreads>(kStSelCap - kBatch * kStBootThreads, kInfBits);
+        bthr = tk.threshold();
     }
     __syncthreads();
     tk.flush<kStBootThreads>(kInfBits);
@@ -277,9 +284,11 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
 // ------------------------------------------------------------------------------------------------------------------
 // A: the filter
 // ------------------------------------------------------------------------------------------------------------------
-struct StCtrl {            // 32 bytes
+struct StCtrl {            // 64 bytes
     int work;
     int pad_[7];
+    float na[kQlQ];        // -astep of the work item's queries
+    float tb[kQlQ];        // threshold constants
 };
 
 template <int M>
@@ -338,24 +347,24 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
         const uint16_t* sp = ql.snorm + grp.beg;
         // first codes in flight before the set-up work
         QlCode<M> c0 = ql_load_code<M>(lp, sp, tid, n), c1 = ql_load_code<M>(lp, sp, kT + tid, n), c2, c3;
-        // pair constants (every thread computes its own copy)
-        float na[Q], tb[Q];
-        {
+        // pair constants: one thread per query, through shared memory (read after the barrier below)
+        if (tid < Q) {
+            const int q = tid;
+            const QlGroup* g = &s_grp[buf];          // (dynamic index: read the shared-memory copy)
+            const bool has = g->pair[q] >= 0;
+            const int pr = has ? g->pair[q] : g->pair[0];
+            const int qq = has ? g->query[q] : g->query[0];
             const float c_sm = __ldg(ql.sbmin + list), c_st = __ldg(ql.sbstep + list);
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-                const int pr = (vmask >> q) & 1u ? grp.pair[q] : grp.pair[0];
-                const float a = __ldg(st.pdis + pr);
-                const float c_am = __ldg(ql.qamin + qi[q]), c_s = __ldg(ql.qscale + qi[q]);
-                const uint32_t thr = __ldg(p.qthr + qi[q]);
-                const float dis0 = a * (1.0f - static_cast<float>(p.d + 5) * 5.9604645e-8f);
-                const float rn = sqrtf(a) * 1.00001f + ql.pmax;
-                const float E = static_cast<float>(dsub + M + 8) * 5.9604645e-8f * rn * rn * 1.00001f;
-                const float mag = fabsf(E) + fabsf(dis0) + fabsf(c_am) + fabsf(c_sm);
-                const float base = (((E - dis0) - c_am) - c_sm) + 4.8e-7f * mag;
-                na[q] = -(c_s * c_st * 0.999999f);
-                tb[q] = (vmask >> q) & 1u ? ql_threshold_const(thr, c_s, base, mag) : -INFINITY;
-            }
+            const float a = __ldg(st.pdis + pr);
+            const float c_am = __ldg(ql.qamin + qq), c_s = __ldg(ql.qscale + qq);
+            const uint32_t thr = __ldg(p.qthr + qq);
+            const float dis0 = a * (1.0f - static_cast<float>(p.d + 5) * 5.9604645e-8f);
+            const float rn = sqrtf(a) * 1.00001f + ql.pmax;
+            const float E = static_cast<float>(dsub + M + 8) * 5.9604645e-8f * rn * rn * 1.00001f;
+            const float mag = fabsf(E) + fabsf(dis0) + fabsf(c_am) + fabsf(c_sm);
+            const float base = (((E - dis0) - c_am) - c_sm) + 4.8e-7f * mag;
+            ctrl->na[q] = -(c_s * c_st * 0.999999f);
+            ctrl->tb[q] = has ? ql_threshold_const(thr, c_s, base, mag) : -INFINITY;
         }
         // the four queries' tables, interleaved entry-wise (see scan_qlut_kernel)
         {
@@ -390,6 +399,12 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
         buf ^= 1;
         if (tid == 0 && next_work < ngroups)
             ql_copy_group_async(&s_grp[buf], static_cast<const QlGroup*>(p.groups) + next_work);
+        float na[Q], tb[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            na[q] = ctrl->na[q];
+            tb[q] = ctrl->tb[q];
+        }
 
         auto test = [&](const QlCode<M>& c) -> uint32_t {
             uint2 lb = ql_block16(lutb, c.v[0], x8, x4, bsel, offs);

@@ -132,9 +132,14 @@ B200_API int b200_ivfpq_get_stage_ms(b200_ivfpq_t h, float* h_ms5);
  * synchronises the stream of that search. */
 B200_API int b200_ivfpq_get_last_scan_stats(b200_ivfpq_t h, int64_t* h_bytes, int64_t* h_codes);
 
-/* instrumentation of the per-query-table filter scan (csrc/scan_qlut.cuh), accumulated over the searches since the
- * last reset when the handle was created with B200_IVFPQ_QL_STATS=1: [0] survivor entries queued by the integer
- * filter, [1] exact fp32 evaluations, [2] work items.  All zero when the statistics are off.  Synchronises. */
+/* device time (ms) of the streaming pipeline's filter kernel (csrc/scan_stream.cuh st_filter_kernel, the kernel the
+ * roofline is quoted on) in the last timed search; B200_IVFPQ_ESTATE if that search did not run it. */
+B200_API int b200_ivfpq_get_filter_ms(b200_ivfpq_t h, float* h_ms);
+
+/* instrumentation of the per-query-table filter scan (csrc/scan_qlut.cuh, csrc/scan_stream.cuh): [0] survivor records the integer
+ * filter passed, [1] exact fp32 evaluations, [2] record chunks used by the streaming pipeline in the last search, or
+ * minus the overflow bits when its fallback launches answered (part of) the batch; in-kernel path (B200_IVFPQ_STREAM=0,
+ * handle created with B200_IVFPQ_QL_STATS=1): work items, accumulated since the last reset.  Synchronises. */
 B200_API int b200_ivfpq_get_filter_stats(b200_ivfpq_t h, int64_t* h_out3, int reset);
 
 #ifdef __cplusplus

@@ -31,7 +31,20 @@ def test_reference_arm_line(oracle):
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["config"]["index"] == "IVF1024,PQ16x8" and d["config"]["batch"] == 10000
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.timeout(900)
+def test_reference_arm_uses_all_cores_under_torchrun(oracle):
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must still use every host core (round 1's N >= 2
+    ratios were inflated by a single-threaded reference)."""
+    p = _run("--impl", "reference", "--config", "c1", "--steps", "1", "--warmup", "1", "--nq", "200",
+             env={"OMP_NUM_THREADS": "1"})
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([ln for ln in p.stdout.splitlines() if ln.strip()][0])
+    ncpu = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == ncpu, (d["cpu_baseline"], ncpu)
 
 
 def test_our_arm_fails_loudly_without_cuda():
