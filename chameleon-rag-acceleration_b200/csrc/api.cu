@@ -480,7 +480,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             const double visits = (double)npairs * (double)h->ntotal / (double)std::max<int64_t>(h->nonempty, 1);
             const double want = std::min(std::max(visits * h->st_rate, h->st_minrec), 192.0 * 1048576.0);
             sb.max_chunks = (unsigned int)(want / kStChunkRecords);
-            sb.capq = h->st_capq > 0 ? h->st_capq : std::max(2048, 32 * k);
+            sb.capq = h->st_capq > 0 ? h->st_capq : std::max(4096, 32 * k);
             if ((rc = h->st_srec.ensure((size_t)sb.max_chunks * kStChunkRecords * 8))) return rc;
             if ((rc = h->st_sfill.ensure((size_t)sb.max_chunks * 4))) return rc;
             if ((rc = h->st_ctr.ensure(kStCtrBytes))) return rc;

@@ -1,4 +1,7 @@
 // qlut.cu -- translation unit of the per-query-table filter scan (scan_qlut.cuh): kernels + their launchers.
+#include <algorithm>
+#include <cstdlib>
+
 #include "qlut_api.h"
 #include "scan_qlut.cuh"
 #include "scan_stream.cuh"
@@ -44,13 +47,16 @@ int ql_launch_scan_t(const ScanParams& sp, const QlParams& ql, int grid, cudaStr
 template <int M>
 int ql_query_tables_t(const float* xq, int64_t nq, const float* pq, const float* mu, const float* pq_maxnorm, int d,
                       int dsub, uint16_t* qlut, float* qscale, float* qamin, cudaStream_t st) {
+    const char* dbg = getenv("B200_IVFPQ_QL_QMAX");   // experiments: coarser table entries (results do not change)
+    const unsigned dbg_qmax = dbg ? (unsigned)atoi(dbg) : 0u;
+    const uint32_t qmax = dbg_qmax ? std::min<uint32_t>(dbg_qmax, QlCfg<M>::kQMax) : QlCfg<M>::kQMax;
     constexpr int QB = 64 / M;
     const size_t smem = sizeof(float) * QB * d;
     auto kernel = ql_query_tables_kernel<M>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -1;
-    kernel<<<(unsigned)((nq + QB - 1) / QB), 256, smem, st>>>(xq, nq, pq, mu, pq_maxnorm, d, dsub, qlut, qscale, qamin);
+    kernel<<<(unsigned)((nq + QB - 1) / QB), 256, smem, st>>>(xq, nq, pq, mu, pq_maxnorm, d, dsub, qmax, qlut, qscale, qamin);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -156,12 +162,29 @@ int st_filter_grid_t(int64_t npairs, int num_sms) {
 template <int M>
 int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
                 cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
-    const size_t bsm = st_boot_smem(sp.d, M, sp.nprobe, sp.k);
-    if (bsm > 48 * 1024 &&
-        cudaFuncSetAttribute(st_boot_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm) != cudaSuccess)
-        return -1;
-    st_boot_kernel<M><<<(unsigned)nq, kStBootThreads, bsm, st>>>(sp.xq, sp.cent, sp.pq, sp.offsets, sp.codes, sp.probe,
-                                                                 sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr);
+    if (sp.k <= 128 && getenv("B200_IVFPQ_BOOT_BLOCK") == nullptr) {
+        // warp-level bootstrap: W winners per warp, 8 W >= 2 k exact candidates
+        const int W = sp.k <= 32 ? 8 : sp.k <= 64 ? 16 : 32;
+        const size_t bsm = st_bootw_smem<M>(sp.d, sp.nprobe, W);
+#define ST_BOOTW(WW)                                                                                                 \
+    {                                                                                                                \
+        auto kernel = st_boot_warp_kernel<M, WW>;                                                                    \
+        if (bsm > 48 * 1024 &&                                                                                       \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm) != cudaSuccess)      \
+            return -1;                                                                                               \
+        kernel<<<(unsigned)nq, kStBootThreads, bsm, st>>>(sp.xq, sp.cent, sp.pq, sp.offsets, sp.codes, sp.probe,     \
+                                                          sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr);         \
+    }
+        if (W == 8) ST_BOOTW(8) else if (W == 16) ST_BOOTW(16) else ST_BOOTW(32)
+#undef ST_BOOTW
+    } else {
+        const size_t bsm = st_boot_smem(sp.d, M, sp.nprobe, sp.k);
+        if (bsm > 48 * 1024 &&
+            cudaFuncSetAttribute(st_boot_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm) != cudaSuccess)
+            return -1;
+        st_boot_kernel<M><<<(unsigned)nq, kStBootThreads, bsm, st>>>(sp.xq, sp.cent, sp.pq, sp.offsets, sp.codes, sp.probe,
+                                                                     sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr);
+    }
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
     const size_t fsm = st_filter_smem<M>();
     if (cudaFuncSetAttribute(st_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
@@ -175,7 +198,7 @@ int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, i
     if (ssm > 48 * 1024 &&
         cudaFuncSetAttribute(st_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm) != cudaSuccess)
         return -1;
-    st_select_kernel<<<(unsigned)nq, kThreads, ssm, st>>>(stp, sp.probe, sp.offsets, sp.nprobe, sp.k);
+    st_select_kernel<<<(unsigned)nq, kStSelThreads, ssm, st>>>(stp, sp.probe, sp.offsets, sp.nprobe, sp.k);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -216,6 +239,10 @@ int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers&
     stp.prefix = static_cast<uint32_t*>(sb.prefix);
     stp.pdis = static_cast<float*>(sb.pdis);
     stp.ids = ids;
+    {
+        const char* bc = getenv("B200_IVFPQ_BOOT_CODES");
+        stp.boot_codes = bc ? std::max(64, std::min(kStBootCodes, atoi(bc))) : kStBootCodes;
+    }
     stp.D = D;
     stp.I = I;
     if (cudaMemsetAsync(sb.ctr, 0, kStCtrBytes, st) != cudaSuccess) return -1;

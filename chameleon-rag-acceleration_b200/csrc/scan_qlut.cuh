@@ -12,12 +12,12 @@
 //
 // (mu = mean of the coarse centroids, any fixed vector works).  Nothing in it depends on the PAIR except one scalar:
 //   * A_q is built ONCE per query and batch (ql_query_tables_kernel), quantised to 11 / 10 / 9 bits for M = 16 / 32 /
-//     64:  u[m][c] = floor((A[m][c] - min_c A[m][.]) * s_q);  a work item only copies the tables of its queries into
-//     shared memory (8 KB per query at M = 16, from L2);
+//     64:  u[m][c] = floor((A[m][c] + B_m) * s_q), B_m >= |A[m][.]| (Cauchy-Schwarz);  a work item only copies the
+//     tables of its queries into shared memory (8 KB per query at M = 16, from L2);
 //   * SB is built ONCE per stored vector when the lists are installed (ql_sb_build_kernel, float64), kept as 16 bits
 //     on a per-list grid, rounded DOWN:  SB >= sbmin[l] + sbstep[l] * v;
 //   * a code can only be among the results if
-//         sum_m u[m][code_m]  <=  s_q * (thr + E - dis0 - sum_m min_m - sbmin - sbstep * v)
+//         sum_m u[m][code_m]  <=  s_q * (thr + E - dis0 + sum_m B_m - sbmin - sbstep * v)
 //     (thr: the query's current k-th best distance; E: rounding slack, below).  The left side is the same
 //     conflict-free packed-integer look-up sum as scan_quad.cuh (one LDS.64 serves four queries); the right side is
 //     one FFMA per (code, query), compared in the "magic number" float domain (2^23 + integer) so that no
@@ -34,7 +34,7 @@
 //     Pmax >= ||p|| for every code word (errors of fl(q - c) - p, of the squares and of the two nested sequential sums);
 //   * dis0 is summed from the same r: real ||q - c||^2 >= dis0 (1 - (d + 5) 2^-24);
 //   * A is evaluated with fp32 FMAs: |A_fl - A_real| <= (dsub + 3) 2^-23 ||(q - mu)_m|| ||pq[m][c]||, summed over m and
-//     taken off sum_m min_m once per query; the quantiser multiplies by (1 - 2^-20) before the floor;
+//     taken off the sum of the offsets once per query; the quantiser multiplies by (1 - 2^-20) before the floor;
 //   * SB is evaluated in float64 from the fp32 inputs (products exact, sums to 2^-53) and the grid point is checked
 //     against it in float64 before it is stored;
 //   * the pair constants are rounded up by 2^-21 of the magnitudes involved, the threshold by another +2 units.
@@ -229,22 +229,23 @@ __global__ void __launch_bounds__(256) ql_mean_kernel(const float* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------------------------
 // Query side: A_q[m][c] = -2 (q - mu)_m . pq[m][c] for QB = 64 / M queries per CTA (thread = code value c, the
-// codebook row is loaded once for all of them), quantised with the query's own scale.
-//   lut[q][c][m] = min(qmax, floor((A - min_c A[m][.]) * s_q (1 - 2^-20)))     s_q = qmax / (1.0001 max_m range_m)
-//   amin[q]      = sum_m min_c A[m][.]  -  (dsub + 3) 2^-23 sum_m ||(q - mu)_m|| max_c ||pq[m][c]||  -  fl slack
+// codebook row is loaded once for all of them), quantised with the query's own scale.  Offsets and scale come from
+// the Cauchy-Schwarz bound |A[m][c]| <= B_m = 2 ||(q - mu)_m|| max_c ||pq[m][c]|| -- no reduction over the 256 code
+// values is needed, at the price of at most one bit of the entries' range:
+//   lut[q][c][m] = min(qmax, floor((A + B_m) * s_q (1 - 2^-20)))               s_q = qmax / (1.0001 max_m 2 B_m)
+//   amin[q]      = - sum_m B_m  -  (dsub + 3) 2^-23 sum_m ||(q - mu)_m|| max_c ||pq[m][c]||  -  fl slack
 // ------------------------------------------------------------------------------------------------------------------
 template <int M>
 __global__ void __launch_bounds__(256) ql_query_tables_kernel(const float* __restrict__ xq, int64_t nq,
                                                               const float* __restrict__ pq, const float* __restrict__ mu,
                                                               const float* __restrict__ pq_maxnorm, int d, int dsub,
-                                                              uint16_t* __restrict__ lut, float* __restrict__ scale,
-                                                              float* __restrict__ amin) {
+                                                              uint32_t qmax, uint16_t* __restrict__ lut,
+                                                              float* __restrict__ scale, float* __restrict__ amin) {
     constexpr int QB = 64 / M;
-    constexpr float kQ = static_cast<float>(QlCfg<M>::kQMax);
+    const float kQ = static_cast<float>(qmax);
     extern __shared__ float ql_qc[];                 // [QB][d]  q - mu
-    __shared__ float red_min[8][QB][M], red_max[8][QB][M];
-    __shared__ float s_min[QB][M], s_scale[QB];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ float s_B[QB][M], s_scale[QB];
+    const int tid = threadIdx.x;
     const int64_t q0 = static_cast<int64_t>(blockIdx.x) * QB;
     for (int e = tid; e < QB * d; e += 256) {
         const int qb = e / d, j = e % d;
@@ -252,84 +253,63 @@ __global__ void __launch_bounds__(256) ql_query_tables_kernel(const float* __res
         ql_qc[e] = __fsub_rn(xq[q * d + j], mu[j]);
     }
     __syncthreads();
-    float A[QB][M];
-#pragma unroll
-    for (int m = 0; m < M; m++) {
-        const float* p = pq + (static_cast<int64_t>(m) * 256 + tid) * dsub;
-        float acc[QB];
-#pragma unroll
-        for (int qb = 0; qb < QB; qb++) acc[qb] = 0.0f;
-        for (int j = 0; j < dsub; j++) {
-            const float pj = __ldg(p + j);
-#pragma unroll
-            for (int qb = 0; qb < QB; qb++) acc[qb] = fmaf(ql_qc[qb * d + m * dsub + j], pj, acc[qb]);
-        }
-#pragma unroll
-        for (int qb = 0; qb < QB; qb++) {
-            A[qb][m] = -2.0f * acc[qb];
-            float lo = A[qb][m], hi = A[qb][m];
-            for (int o = 16; o > 0; o >>= 1) {
-                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            }
-            if (lane == 0) {
-                red_min[wid][qb][m] = lo;
-                red_max[wid][qb][m] = hi;
-            }
-        }
-    }
-    __syncthreads();
     if (tid < QB * M) {
         const int qb = tid / M, m = tid % M;
-        float lo = red_min[0][qb][m], hi = red_max[0][qb][m];
-        for (int w = 1; w < 8; w++) {
-            lo = fminf(lo, red_min[w][qb][m]);
-            hi = fmaxf(hi, red_max[w][qb][m]);
-        }
-        s_min[qb][m] = lo;
-        // this sub-quantizer's share of the rounding slack and its range
         float nn = 0.0f;
         for (int j = 0; j < dsub; j++) nn = fmaf(ql_qc[qb * d + m * dsub + j], ql_qc[qb * d + m * dsub + j], nn);
-        red_max[0][qb][m] = hi - lo;                                  // range
-        red_max[1][qb][m] = sqrtf(nn) * 1.00001f * pq_maxnorm[m];     // error weight
+        s_B[qb][m] = 2.0f * sqrtf(nn) * 1.0001f * pq_maxnorm[m];      // >= |A[m][c]| for every c
     }
     __syncthreads();
     if (tid < QB) {
         const int qb = tid;
-        float range = 0.0f, err = 0.0f, slo = 0.0f, alo = 0.0f;
+        float range = 0.0f, sumB = 0.0f;
         for (int m = 0; m < M; m++) {
-            range = fmaxf(range, red_max[0][qb][m]);
-            err += red_max[1][qb][m];
-            slo += s_min[qb][m];
-            alo += fabsf(s_min[qb][m]);
+            range = fmaxf(range, 2.0f * s_B[qb][m]);
+            sumB += s_B[qb][m];
         }
         // finite check: NaN / inf queries get scale 0 (nothing is filtered, the exact path decides)
-        const bool ok = range > 0.0f && range < 1.0e30f && alo < 1.0e30f;
+        const bool ok = range > 0.0f && range < 1.0e30f && sumB < 1.0e30f;
         const float s = ok ? (kQ / (range * 1.0001f)) : 0.0f;
         s_scale[qb] = s;
         if (q0 + qb < nq) {
             scale[q0 + qb] = s;
-            const float slack = static_cast<float>(dsub + 3) * 1.1920929e-7f * err * 1.0001f +
-                                alo * 1.2e-7f * static_cast<float>(M);
-            amin[q0 + qb] = ok ? slo - slack : 0.0f;
+            // rounding of the fp32 dot products ((dsub + 3) 2^-23 of |q_m| |p|, i.e. of B_m / 2) + of this sum
+            const float slack = static_cast<float>(dsub + 3) * 1.1920929e-7f * sumB + sumB * 1.2e-7f * static_cast<float>(M);
+            amin[q0 + qb] = ok ? -(sumB + slack) : 0.0f;
         }
     }
     __syncthreads();
+    uint32_t w[QB][M / 2];
+#pragma unroll
+    for (int m = 0; m < M; m += 2) {
+        float acc[QB][2];
+#pragma unroll
+        for (int qb = 0; qb < QB; qb++) acc[qb][0] = acc[qb][1] = 0.0f;
+        const float* p0 = pq + (static_cast<int64_t>(m) * 256 + tid) * dsub;
+        const float* p1 = p0 + 256 * dsub;
+        for (int j = 0; j < dsub; j++) {
+            const float a = __ldg(p0 + j), b = __ldg(p1 + j);
+#pragma unroll
+            for (int qb = 0; qb < QB; qb++) {
+                acc[qb][0] = fmaf(ql_qc[qb * d + m * dsub + j], a, acc[qb][0]);
+                acc[qb][1] = fmaf(ql_qc[qb * d + (m + 1) * dsub + j], b, acc[qb][1]);
+            }
+        }
+#pragma unroll
+        for (int qb = 0; qb < QB; qb++) {
+            const float s2 = s_scale[qb] * 0.999999f;
+            const float x0 = (-2.0f * acc[qb][0] + s_B[qb][m]) * s2, x1 = (-2.0f * acc[qb][1] + s_B[qb][m + 1]) * s2;
+            const uint32_t u0 = x0 > 0.0f ? min(static_cast<uint32_t>(__float2uint_rz(x0)), qmax) : 0u;
+            const uint32_t u1 = x1 > 0.0f ? min(static_cast<uint32_t>(__float2uint_rz(x1)), qmax) : 0u;
+            w[qb][m / 2] = u0 | (u1 << 16);
+        }
+    }
 #pragma unroll
     for (int qb = 0; qb < QB; qb++) {
         if (q0 + qb >= nq) break;
-        const float s2 = s_scale[qb] * 0.999999f;
-        uint32_t w[M / 2];
-#pragma unroll
-        for (int m = 0; m < M; m += 2) {
-            const float x0 = (A[qb][m] - s_min[qb][m]) * s2, x1 = (A[qb][m + 1] - s_min[qb][m + 1]) * s2;
-            const uint32_t u0 = x0 > 0.0f ? min(static_cast<uint32_t>(__float2uint_rz(x0)), QlCfg<M>::kQMax) : 0u;
-            const uint32_t u1 = x1 > 0.0f ? min(static_cast<uint32_t>(__float2uint_rz(x1)), QlCfg<M>::kQMax) : 0u;
-            w[m / 2] = u0 | (u1 << 16);
-        }
         uint4* dst = reinterpret_cast<uint4*>(lut + ((q0 + qb) * 256 + tid) * M);
 #pragma unroll
-        for (int i = 0; i < M / 8; i++) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        for (int i = 0; i < M / 8; i++) dst[i] = make_uint4(w[qb][4 * i], w[qb][4 * i + 1], w[qb][4 * i + 2], w[qb][4 * i + 3]);
     }
 }
 

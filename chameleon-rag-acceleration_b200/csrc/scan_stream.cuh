@@ -35,6 +35,7 @@ constexpr int kStChunk = 64;          // survivor records per chunk
 constexpr int kStBootCodes = 2048;    // codes (in scan order) the bootstrap looks at
 constexpr int kStBootThreads = 256;
 constexpr int kStSelCap = 2048;
+constexpr int kStSelThreads = 128;
 
 struct StCounters {
     unsigned int nchunks;             // chunks handed out
@@ -61,6 +62,7 @@ struct StParams {
     uint32_t* prefix;                 // (nq, nprobe) scan position of the first code of every probed list
     float* pdis;                      // (nq, nprobe) ||fl(q - c)||^2
     const int64_t* ids;
+    int boot_codes;                   // candidates the bootstrap looks at (<= kStBootCodes)
     float* D;                         // (nq, k)
     int64_t* I;
 };
@@ -192,7 +194,7 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
     __syncthreads();
     // candidates: the first codes in scan order, ranked by the estimated distance dis0 + SB + sum_m A; all of them
     // go to the queue (it holds kStBootCodes keys), one fold at the end
-    const uint32_t ncand = static_cast<uint32_t>(s_total < kStBootCodes ? s_total : kStBootCodes);
+    const uint32_t ncand = static_cast<uint32_t>(s_total < static_cast<unsigned long long>(st.boot_codes) ? s_total : st.boot_codes);
     const float sq = ql.qscale[q], aq = ql.qamin[q];
     const float inv = sq > 0.0f ? 1.0f / sq : 0.0f;
     constexpr int kPer = kStBootCodes / kStBootThreads;   // 8 candidates per thread
@@ -278,6 +280,234 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
         }
         qthr[q] = t;
         st.qkey[q] = tkey;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// S, fast form for k <= 4 W (W = 8, 16, 32 winners per warp): no block-level selection at all.  Every warp ranks its
+// 256 candidates by the estimate, keeps its W best (W rounds of a warp arg-min), evaluates them exactly with 16 lanes
+// per candidate (lane = sub-quantizer; the 16 partial sums are then added one after the other in the oracle's order,
+// so the distance is the oracle's bit for bit), and warp 0 sorts the 8 W exact keys: their k-th smallest is the
+// threshold.  Three barriers per query.
+// ------------------------------------------------------------------------------------------------------------------
+template <int M>
+__host__ __device__ inline size_t st_bootw_smem(int d, int nprobe, int W) {
+    return sizeof(float) * ((d + 3) & ~3) + sizeof(uint16_t) * 256 * (M + 2) + 3 * sizeof(uint32_t) * nprobe +
+           sizeof(int64_t) * nprobe + sizeof(uint64_t) * 8 * W + 64;
+}
+
+template <int M, int W>
+__global__ void __launch_bounds__(kStBootThreads)
+st_boot_warp_kernel(const float* __restrict__ xq, const float* __restrict__ cent, const float* __restrict__ pq,
+                    const int64_t* __restrict__ offsets, const uint8_t* __restrict__ codes,
+                    const int32_t* __restrict__ probe, int nprobe, int d, int dsub, int k, QlParams ql, StParams st,
+                    uint32_t* __restrict__ qthr) {
+    static_assert(M % 16 == 0, "16 lanes per candidate, M / 16 sub-quantizers per lane");
+    extern __shared__ __align__(16) unsigned char smem_boot[];
+    const int dpad = (d + 3) & ~3;
+    constexpr int kRow = M + 2;
+    float* qv = reinterpret_cast<float*>(smem_boot);
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(qv + dpad);                 // [256][M + 2]
+    uint32_t* s_sz = reinterpret_cast<uint32_t*>(s_lut + 256 * kRow);
+    uint32_t* s_pre = s_sz + nprobe;
+    int32_t* s_list = reinterpret_cast<int32_t*>(s_pre + nprobe);
+    uintptr_t al = (reinterpret_cast<uintptr_t>(s_list + nprobe) + 7) & ~static_cast<uintptr_t>(7);
+    int64_t* s_off = reinterpret_cast<int64_t*>(al);                          // first row of every probed list
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_off + nprobe);           // [8 W] exact keys
+    __shared__ unsigned long long s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t q = blockIdx.x;
+    for (int j = tid; j < d; j += kStBootThreads) qv[j] = xq[q * d + j];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(ql.qlut + q * 256 * M);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_lut);
+        for (int i = tid; i < 256 * M / 2; i += kStBootThreads) dst[(i / (M / 2)) * (kRow / 2) + (i % (M / 2))] = __ldg(src + i);
+    }
+    for (int r = tid; r < nprobe; r += kStBootThreads) {
+        const int l = probe[q * nprobe + r];
+        int64_t sz = 0, beg = 0;
+        if (l >= 0) {
+            beg = offsets[l];
+            sz = offsets[l + 1] - beg;
+        }
+        s_list[r] = sz > 0 ? l : -1;
+        s_sz[r] = static_cast<uint32_t>(sz > 0 ? sz : 0);
+        s_off[r] = beg;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long carry = 0ull;
+        for (int r0 = 0; r0 < nprobe; r0 += 32) {
+            const int r = r0 + lane;
+            const unsigned long long v = r < nprobe ? s_sz[r] : 0u;
+            unsigned long long x = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (r < nprobe) {
+                const unsigned long long pre = carry + x - v;
+                s_pre[r] = static_cast<uint32_t>(pre);
+                st.prefix[q * nprobe + r] = static_cast<uint32_t>(pre);
+            }
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) {
+            s_total = carry;
+            if (carry >= (1ull << 32)) atomicOr(&st.ctr->overflow, 1);
+            st.qcnt[q] = 0u;
+            st.qflag[q] = 0;
+        }
+    }
+    for (int r = wid; r < nprobe; r += kStBootThreads / 32) {
+        const int l = s_list[r];
+        float a = 0.0f;
+        if (l >= 0) {
+            for (int j = lane; j < d; j += 32) {
+                const float rj = __fsub_rn(qv[j], __ldg(cent + static_cast<int64_t>(l) * d + j));
+                a = fmaf(rj, rj, a);
+            }
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        }
+        if (lane == 0) st.pdis[q * nprobe + r] = a;
+    }
+    __syncthreads();
+    const uint32_t ncand = static_cast<uint32_t>(s_total < static_cast<unsigned long long>(st.boot_codes) ? s_total : st.boot_codes);
+    const float sq = ql.qscale[q], aq = ql.qamin[q];
+    const float inv = sq > 0.0f ? 1.0f / sq : 0.0f;
+    constexpr int kPer = kStBootCodes / kStBootThreads;   // 8 candidates per lane: positions i * 256 + tid
+    uint32_t est[kPer];
+    {
+        uint4 cv[kPer][M / 16];
+        float add[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const uint32_t pos = i * kStBootThreads + tid;
+            add[i] = 0.0f;
+#pragma unroll
+            for (int h = 0; h < M / 16; h++) cv[i][h] = make_uint4(0u, 0u, 0u, 0u);
+            if (pos < ncand) {
+                int r = 0;
+                while (r + 1 < nprobe && s_pre[r + 1] <= pos) r++;
+                const int l = s_list[r];
+                const int64_t row = s_off[r] + (pos - s_pre[r]);
+                const uint4* cp = reinterpret_cast<const uint4*>(codes + row * M);
+#pragma unroll
+                for (int h = 0; h < M / 16; h++) cv[i][h] = __ldg(cp + h);
+                add[i] = st.pdis[q * nprobe + r] + __ldg(ql.sbmin + l) +
+                         __ldg(ql.sbstep + l) * static_cast<float>(__ldg(ql.snorm + row)) + aq;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const uint32_t pos = i * kStBootThreads + tid;
+            uint32_t u = 0u;
+#pragma unroll
+            for (int h = 0; h < M / 16; h++) {
+                const uint32_t w[4] = {cv[i][h].x, cv[i][h].y, cv[i][h].z, cv[i][h].w};
+#pragma unroll
+                for (int mm = 0; mm < 16; mm++)
+                    u += s_lut[((w[mm >> 2] >> (8 * (mm & 3))) & 255u) * kRow + 16 * h + mm];
+            }
+            const float e = add[i] + static_cast<float>(u) * inv;
+            uint32_t bits = __float_as_uint(fmaxf(e, 0.0f));
+            if (!(e == e)) bits = 0x7f7fffffu;
+            est[i] = pos < ncand ? bits : 0xffffffffu;
+        }
+    }
+    // W rounds of a warp arg-min over the 8 x 32 estimates; the winners' positions end up in wpos (lane i holds
+    // winner i; W <= 32)
+    uint32_t wpos = 0xffffffffu;
+#pragma unroll 1
+    for (int rnd = 0; rnd < W; rnd++) {
+        uint32_t best = est[0];
+        int bi = 0;
+#pragma unroll
+        for (int i = 1; i < kPer; i++)
+            if (est[i] < best) {
+                best = est[i];
+                bi = i;
+            }
+        // (estimate, lane) minimum over the warp
+        uint64_t key = (static_cast<uint64_t>(best) << 32) | static_cast<uint32_t>(lane);
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        const int wl = static_cast<int>(key & 31u);
+        const bool valid = static_cast<uint32_t>(key >> 32) != 0xffffffffu;
+        const uint32_t p = __shfl_sync(0xffffffffu, static_cast<uint32_t>(bi * kStBootThreads + tid), wl);
+        if (lane == rnd) wpos = valid ? p : 0xffffffffu;
+        if (lane == wl) {
+#pragma unroll
+            for (int i = 0; i < kPer; i++)
+                if (i == bi) est[i] = 0xffffffffu;
+        }
+    }
+    // exact distances: 16 lanes per winner (lane & 15 = sub-quantizer group), two winners per pass
+    const int sub = lane & 15, half = lane >> 4;
+#pragma unroll 1
+    for (int pass = 0; pass < W / 2; pass++) {
+        const int widx = 2 * pass + half;
+        const uint32_t pos = __shfl_sync(0xffffffffu, wpos, widx);
+        float tsum[M / 16];
+        int l = -1;
+        int64_t row = 0;
+        if (pos != 0xffffffffu) {
+            int r = 0;
+            while (r + 1 < nprobe && s_pre[r + 1] <= pos) r++;
+            l = s_list[r];
+            row = s_off[r] + (pos - s_pre[r]);
+        }
+#pragma unroll
+        for (int h = 0; h < M / 16; h++) {
+            const int m = 16 * h + sub;
+            float t = 0.0f;
+            if (l >= 0) {
+                const uint32_t cvb = __ldg(codes + row * M + m);
+                const float* pc = pq + (static_cast<int64_t>(m) * 256 + cvb) * dsub;
+                const float* cc = cent + static_cast<int64_t>(l) * d + m * dsub;
+                for (int j = 0; j < dsub; j++) t = sqdiff_acc(t, __fsub_rn(qv[m * dsub + j], __ldg(cc + j)), __ldg(pc + j));
+            }
+            tsum[h] = t;
+        }
+        // sum over m in ascending order: m = 16 h + s, s = 0..15, through the 16 lanes of the group
+        float acc = 0.0f;
+#pragma unroll
+        for (int h = 0; h < M / 16; h++) {
+#pragma unroll
+            for (int sidx = 0; sidx < 16; sidx++) {
+                const float t = __shfl_sync(0xffffffffu, tsum[h], (lane & 16) | sidx);
+                acc = __fadd_rn(acc, t);
+            }
+        }
+        if (sub == 0) s_keys[wid * W + widx] = l >= 0 ? make_key(__float_as_uint(acc), pos) : kPadKey;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        constexpr int R = W / 4;          // 8 W keys = 32 R
+        uint64_t v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = s_keys[32 * r + lane];
+        TopK::warp_sort<R>(v, lane);
+        // element e = 32 r + lane is v[r]: the k-th smallest is element k - 1
+        const int e = k - 1;
+        uint64_t kth = kPadKey;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint64_t x = __shfl_sync(0xffffffffu, v[r], e & 31);
+            if (r == (e >> 5)) kth = x;
+        }
+        if (lane == 0) {
+            uint32_t t = kInfBits;
+            uint64_t tkey = kPadKey;
+            if (kth != kPadKey && static_cast<uint32_t>(kth >> 32) < kInfBits) {
+                t = static_cast<uint32_t>(kth >> 32);
+                tkey = kth;
+            }
+            qthr[q] = t;
+            st.qkey[q] = tkey;
+        }
     }
 }
 
@@ -520,7 +750,7 @@ st_eval_kernel(const ScanParams p, const StParams st) {
 // ------------------------------------------------------------------------------------------------------------------
 // C: per-query selection + id lookup
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kStSelThreads)
 st_select_kernel(const StParams st, const int32_t* __restrict__ probe, const int64_t* __restrict__ offsets, int nprobe,
                  int k) {
     if (threadIdx.x == 0) {
@@ -541,23 +771,23 @@ st_select_kernel(const StParams st, const int32_t* __restrict__ probe, const int
     const unsigned int n = min(st.qcnt[q], static_cast<unsigned int>(st.capq));
     const uint64_t* keys = st.slab + static_cast<size_t>(q) * st.capq;
     uint32_t thr = kInfBits;
-    for (unsigned int base = 0; base < n; base += kThreads * 4) {
+    for (unsigned int base = 0; base < n; base += kStSelThreads * 4) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const unsigned int i = base + u * kThreads + tid;
+            const unsigned int i = base + u * kStSelThreads + tid;
             uint64_t key = kPadKey;
             if (i < n) key = keys[i];
             tk.push(i < n && static_cast<uint32_t>(key >> 32) <= thr, key);
         }
-        tk.sync_and_flush_if_over<kThreads>(kStSelCap - kThreads * 4, kInfBits);
+        tk.sync_and_flush_if_over<kStSelThreads>(kStSelCap - kStSelThreads * 4, kInfBits);
         thr = tk.threshold();
     }
     __syncthreads();
-    tk.flush<kThreads>(kInfBits);
+    tk.flush<kStSelThreads>(kInfBits);
     const int nb = tk.count();
     const uint64_t* s = tk.sorted();
     const uint32_t* pre = st.prefix + q * nprobe;
-    for (int i = tid; i < k; i += kThreads) {
+    for (int i = tid; i < k; i += kStSelThreads) {
         float dv = FLT_MAX;
         int64_t id = -1;
         if (i < nb) {
