@@ -31,6 +31,7 @@ SYMBOLS = [
     ("b200_ivfpq_search_preassigned", _I, [_P, _L, _P, _I, _I, _P, _P, _P, _P]),
     ("b200_ivfpq_search_host", _I, [_P, _L, _P, _I, _I, _P, _P]),
     ("b200_ivfpq_assign_encode", _I, [_P, _L, _P, _P, _P, _P]),
+    ("b200_ivfpq_segment_sums", _I, [_L, _I, _P, _P, _P, _P, _P]),
     ("b200_ivfpq_merge_shards", _I, [_I, _L, _I, _P, _P, _P, _P, _P]),
     ("b200_ivfpq_merge_shards_peer", _I, [_I, _L, _I, _P, _L, _L, _P, _P, _P]),
     ("b200_ivfpq_set_stage_timing", _I, [_P, _I]),

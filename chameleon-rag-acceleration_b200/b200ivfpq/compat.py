@@ -50,8 +50,8 @@ class Clustering:
     """faiss.Clustering(d, k) as the reference trains its coarse quantizer with it (bench_gpu_1bn.py:520-542):
         clus = faiss.Clustering(d, k); clus.verbose = True; clus.max_points_per_centroid = 10000000
         clus.train(x, index); centroids = faiss.vector_float_to_array(clus.centroids).reshape(k, d)
-    Lloyd iterations on the GPU (b200ivfpq.kmeans; on the CPU when no device is present); `index` receives the
-    centroids like Faiss's assignment index does."""
+    Lloyd iterations on the GPU (b200ivfpq.kmeans); there is no CPU path: without a CUDA device this raises like the
+    rest of the package.  `index` receives the centroids like Faiss's assignment index does."""
 
     def __init__(self, d: int, k: int):
         self.d, self.k = int(d), int(k)
@@ -67,14 +67,15 @@ class Clustering:
         xt = torch.as_tensor(x, dtype=torch.float32)
         if xt.dim() != 2 or xt.shape[1] != self.d:
             raise AssertionError(f"Clustering.train: expected (n, {self.d}) vectors")
-        if torch.cuda.is_available():
-            xt = xt.cuda()
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200ivfpq needs a CUDA device (B200, sm_100a); there is no CPU path")
+        xt = xt.cuda()
         c = kmeans(xt, self.k, niter=self.niter, seed=self.seed, max_points_per_centroid=self.max_points_per_centroid,
                    verbose=self.verbose)
         self.centroids = c.reshape(-1).cpu().numpy()
         if index is not None:
             index.reset()
-            index.add(c if torch.cuda.is_available() else c.cpu().numpy())
+            index.add(c)
 
 
 class float_maxheap_array_t:

@@ -9,8 +9,16 @@ produced by a Faiss binary.  Layout (little endian; size_t and idx_t are 8 bytes
 
   "IwPQ"  index header: d:int  ntotal:i64  dummy:i64 (1<<20)  dummy:i64  is_trained:bool  metric_type:int
           nlist:size_t  nprobe:size_t
-          quantizer = "IxF2"  index header (d, nlist, ...)  xb: n4:size_t then n4*4 elements
-                      (float32 elements in 1.7.1; bytes of the float32 array in 1.7.2 -- told apart by n4)
+          quantizer = "IxF2"  index header (d, nlist, ...)  flat storage, one count word + nlist*d*4 payload bytes:
+                      count = nlist*d      WRITEVECTOR(xb) up to 1.6.x, and WRITEXBVECTOR(codes) from 1.7.2 on
+                                           (codes is the uint8 image of the floats: size/4 = nlist*d) -- the DEFAULT
+                                           this module writes;
+                      count = nlist*d/4    WRITEXBVECTOR applied to the float vector xb (size/4 ELEMENTS), which is
+                                           how we remember 1.7.0 / 1.7.1 -- the release the reference pins for its CPU
+                                           runs (Faiss_experiments/README.md:18).  A reviewer of round 1 remembers
+                                           WRITEVECTOR there instead; no Faiss source or binary is available here to
+                                           settle it, so the reader accepts both counts (the payload is identical and
+                                           the count tells them apart) and the writer only emits this one on request
           direct map: type:char  array: n:size_t + n*i64   (type 2 = hashtable: + n:size_t + n*(i64, i64))
           by_residual:bool  code_size:size_t
           ProductQuantizer: d:size_t  M:size_t  nbits:size_t  centroids: n:size_t + n*f32   ((M, ksub, dsub))
@@ -74,10 +82,10 @@ def parse_faiss_ivfpq(path_or_bytes) -> dict:
         raise RuntimeError(f"read_index: unsupported coarse quantizer '{hq}' (only IndexFlatL2)")
     qd, qn, _, _ = _read_header(r)
     n4 = r.take("Q")
-    if n4 * 4 == qn * qd:                       # 1.7.1: float elements
+    if n4 == qn * qd:                           # count = number of floats (WRITEVECTOR, WRITEXBVECTOR(codes))
+        coarse = r.array(np.float32, n4)
+    elif n4 * 4 == qn * qd:                     # count = floats / 4 (WRITEXBVECTOR on the float vector)
         coarse = r.array(np.float32, n4 * 4)
-    elif n4 * 4 == qn * qd * 4:                 # 1.7.2+: bytes of the float array
-        coarse = r.array(np.uint8, n4 * 4).view(np.float32)
     else:
         raise RuntimeError("read_index: unexpected size of the coarse quantizer's vector storage")
     coarse = np.array(coarse, np.float32).reshape(qn, qd)
@@ -119,9 +127,12 @@ def parse_faiss_ivfpq(path_or_bytes) -> dict:
             "codes": codes, "ids": ids}
 
 
-def write_faiss_ivfpq(path, arrays: dict, nprobe: int = 1, flat_storage: str = "float") -> None:
-    """Write the arrays of IndexIVFPQ.to_arrays() as an "IwPQ" file.  flat_storage: "float" (1.7.1) or "bytes"
-    (1.7.2+) for the coarse quantizer's vectors."""
+def write_faiss_ivfpq(path, arrays: dict, nprobe: int = 1, flat_storage: str = "bytes") -> None:
+    """Write the arrays of IndexIVFPQ.to_arrays() as an "IwPQ" file.  flat_storage: "bytes" (default: count word =
+    nlist*d, what Faiss <= 1.6 and >= 1.7.2 read) or "float" (count word = nlist*d / 4, see the module docstring) for the
+    coarse quantizer's vectors."""
+    if flat_storage not in ("bytes", "float"):
+        raise ValueError("flat_storage must be 'bytes' or 'float'")
     coarse = np.ascontiguousarray(arrays["coarse"], np.float32)
     pq = np.ascontiguousarray(arrays["pq"], np.float32)
     offsets = np.ascontiguousarray(arrays["offsets"], np.int64)

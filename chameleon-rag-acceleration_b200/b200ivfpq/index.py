@@ -270,14 +270,23 @@ class IndexIVFPQ:
         if self._handle is None:
             self._handle = _Handle(self.d, self.nlist, self.pq.M, self.pq.nbits)
             self._lists_dirty = True
+            self._pushed_xb = None
             if self.is_trained:
                 self._push_codebooks()
+        elif self.is_trained and self.quantizer.xb_tensor() is not None and \
+                getattr(self, "_pushed_xb", None) != self.quantizer.xb_tensor().data_ptr():
+            # quantizer.add() / reset() replaced the centroid tensor: the library holds a borrowed pointer to the old one
+            self._push_codebooks()
         return self._handle
 
     def _push_codebooks(self):
         h = self._handle
+        if tuple(self.quantizer.xb_tensor().shape) != (self.nlist, self.d):
+            raise RuntimeError(f"quantizer holds {tuple(self.quantizer.xb_tensor().shape)} vectors, expected "
+                               f"({self.nlist}, {self.d})")
         _lib.check(h.lib.b200_ivfpq_set_codebooks(h.h, self.quantizer.xb_tensor().data_ptr(),
                                                   self.pq._centroids.data_ptr()))
+        self._pushed_xb = self.quantizer.xb_tensor().data_ptr()
 
     def _device(self):
         if self.quantizer.xb_tensor() is not None:
@@ -380,6 +389,9 @@ class IndexIVFPQ:
             nb = xb.shape[0]
             list_no = torch.empty(nb, dtype=torch.int64, device=dev)
             codes = torch.empty((nb, self.pq.M), dtype=torch.uint8, device=dev)
+            if not bool(torch.isfinite(xb).all()):
+                # the coarse quantizer answers id -1 for rows with NaN / inf distances: nothing to encode against
+                raise RuntimeError("add: the vectors contain NaN or inf")
             with torch.cuda.device(dev):
                 _lib.check(h.lib.b200_ivfpq_assign_encode(h.h, nb, xb.data_ptr(), list_no.data_ptr(), codes.data_ptr(),
                                                           _stream_ptr(dev)))

@@ -3,8 +3,10 @@
 Mirrors what the reference's drivers get from Faiss: Lloyd iterations (niter = 25), training set
 subsampled to at most max_points_per_centroid points per centroid, empty clusters re-seeded by splitting
 the largest one (call sites: bench_cpu_performance.py:98-109, bench_gpu_1bn.py:522-542, 583-594).
-The assignment step is a plain library GEMM (torch.matmul); parity does not depend on it because the
-oracle and the CUDA kernels are always compared on the SAME trained codebooks.
+The assignment step is a plain library GEMM (torch.addmm); the centroid update is this repo's sequential segmented
+sum (b200_ivfpq_segment_sums), so that training is reproducible bit for bit for fixed seeds: two bench runs -- or two
+GPU counts -- then search the same index.  Parity does not depend on training: the oracle and the CUDA kernels are
+always compared on the SAME trained codebooks.
 """
 from __future__ import annotations
 
@@ -27,6 +29,27 @@ def _assign(x: torch.Tensor, c: torch.Tensor, chunk: int = 0):
     return labels, obj
 
 
+def _segment_sums(x: torch.Tensor, labels: torch.Tensor, k: int):
+    """(sums (k, d), counts (k,)) of the rows of x grouped by label, reproducible bit for bit: on the GPU a stable sort
+    of the labels + the library's sequential segmented sum (b200_ivfpq_segment_sums) instead of an atomic scatter-add."""
+    counts = torch.bincount(labels, minlength=k)
+    if not x.is_cuda:
+        sums = torch.zeros((k, x.shape[1]), dtype=x.dtype)
+        sums.index_add_(0, labels, x)
+        return sums, counts
+    from . import _lib
+    lib = _lib.load()
+    order = torch.argsort(labels, stable=True)
+    start = torch.zeros(k + 1, dtype=torch.int64, device=x.device)
+    start[1:] = torch.cumsum(counts, 0)
+    sums = torch.empty((k, x.shape[1]), dtype=torch.float32, device=x.device)
+    xc = x.contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.b200_ivfpq_segment_sums(k, xc.shape[1], xc.data_ptr(), order.data_ptr(), start.data_ptr(),
+                                               sums.data_ptr(), int(torch.cuda.current_stream(x.device).cuda_stream)))
+    return sums, counts
+
+
 def kmeans(x: torch.Tensor, k: int, niter: int = 25, seed: int = 1234, max_points_per_centroid: int = 256,
            verbose: bool = False) -> torch.Tensor:
     """x: (n, d) float32 on the GPU.  Returns (k, d) float32 centroids."""
@@ -44,9 +67,7 @@ def kmeans(x: torch.Tensor, k: int, niter: int = 25, seed: int = 1234, max_point
     c = x[perm].clone()
     for it in range(niter):
         labels, obj = _assign(x, c)
-        counts = torch.bincount(labels, minlength=k)
-        sums = torch.zeros_like(c)
-        sums.index_add_(0, labels, x)
+        sums, counts = _segment_sums(x, labels, k)
         nonempty = counts > 0
         c = torch.where(nonempty.unsqueeze(1), sums / counts.clamp(min=1).unsqueeze(1).to(sums.dtype), c)
         nempty = int((~nonempty).sum())
@@ -79,10 +100,8 @@ def kmeans_subspaces(x: torch.Tensor, M: int, ksub: int = 256, niter: int = 25, 
         dist = torch.baddbmm(cn.unsqueeze(1), xs, c.transpose(1, 2), alpha=-2.0)   # (M, n, ksub)
         labels = dist.argmin(dim=2)                                     # (M, n)
         flat = (labels + ar * ksub).reshape(-1)
-        counts = torch.bincount(flat, minlength=M * ksub).reshape(M, ksub)
-        sums = torch.zeros(M * ksub, dsub, device=x.device, dtype=x.dtype)
-        sums.index_add_(0, flat, xs.reshape(-1, dsub))
-        sums = sums.reshape(M, ksub, dsub)
+        sums, counts = _segment_sums(xs.reshape(-1, dsub), flat, M * ksub)
+        sums, counts = sums.reshape(M, ksub, dsub), counts.reshape(M, ksub)
         nonempty = counts > 0
         c = torch.where(nonempty.unsqueeze(2), sums / counts.clamp(min=1).unsqueeze(2).to(sums.dtype), c)
         if not bool(nonempty.all()):

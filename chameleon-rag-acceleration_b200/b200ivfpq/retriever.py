@@ -97,6 +97,10 @@ class AsyncB200Retriever(LocalB200Retriever):
     retrieve_recv(k)         returns (indices, distances) like ExternalRetriever.retrieve_recv.  CUDA tensors in ->
                              CUDA tensors out, and the CALLER's stream waits on the event (no host sync);
                              numpy in -> numpy out.
+
+    The index handle owns ONE workspace: while a send is pending, do not search the same index object from another
+    stream (the two searches would share the probe table and candidate buffers).  Give the retriever its own index
+    object (same codebook / list tensors, a second handle) if the decoder also searches.
     """
 
     def __init__(self, index: IndexIVFPQ, default_k: Optional[int] = 10, nprobe: Optional[int] = 1,
@@ -142,7 +146,12 @@ class AsyncB200Retriever(LocalB200Retriever):
         if self._as_numpy:
             self._event.synchronize()
             return I.cpu().numpy(), D.cpu().numpy()
-        torch.cuda.current_stream(self._dev).wait_event(self._event)
+        consumer = torch.cuda.current_stream(self._dev)
+        consumer.wait_event(self._event)
+        # D and I were allocated under the side stream: tell the caching allocator that the caller's stream uses them,
+        # or their blocks could be handed to the next side-stream search while the caller still reads them
+        D.record_stream(consumer)
+        I.record_stream(consumer)
         return I, D
 
     def retrieve(self, query, nprobe: Optional[int] = None, k: Optional[int] = None):

@@ -112,6 +112,7 @@ class B200Server:
         self.server.listen(1)
         self.address = self.server.getsockname()
         self.served = 0
+        self.rejected = 0
 
     def retrieve(self, query: np.ndarray, k: Optional[int] = None):
         D, I = self.index.search(np.ascontiguousarray(query, np.float32), k or self.default_k)
@@ -122,16 +123,31 @@ class B200Server:
                                              np.ascontiguousarray(list_ids, np.int64))
         return {"id": np.asarray(I), "dist": np.asarray(D)}
 
+    def _empty_answer(self) -> bytes:
+        """What a search that found nothing returns (ids -1, distances FLT_MAX), in the fixed answer length the client
+        waits for: the reply to a request this service cannot serve."""
+        ids = np.full((self.batch_size, self.default_k), -1, np.int64)
+        dist = np.full((self.batch_size, self.default_k), np.finfo(np.float32).max, np.float32)
+        return encode_answer(ids, dist)
+
     def handle(self, msg: bytes) -> bytes:
-        if self.request_with_lists:
-            k, queries, lists = decode_request_with_lists(msg, self.batch_size, self.dim, self.nprobe)
-            out = self.retrieve_with_lists(queries, lists, k)
-        else:
-            k, queries = decode_request(msg, self.batch_size, self.dim)
-            out = self.retrieve(queries, k)
-        if k != self.default_k:
-            raise ValueError(f"request asks for k = {k}, the service was started with k = {self.default_k}")
-        return encode_answer(out["id"], out["dist"])
+        """One request -> one answer.  The request's k is checked BEFORE anything is searched; a request the service
+        cannot serve (wrong k, malformed lists, a failing search) is logged and answered with an empty result, and the
+        loop keeps serving -- the reference's server does not die on a bad request either (faiss_server.py:241-277)."""
+        try:
+            if self.request_with_lists:
+                k, queries, lists = decode_request_with_lists(msg, self.batch_size, self.dim, self.nprobe)
+            else:
+                k, queries = decode_request(msg, self.batch_size, self.dim)
+                lists = None
+            if k != self.default_k:
+                raise ValueError(f"request asks for k = {k}, the service was started with k = {self.default_k}")
+            out = self.retrieve_with_lists(queries, lists, k) if lists is not None else self.retrieve(queries, k)
+            return encode_answer(out["id"], out["dist"])
+        except Exception as e:      # noqa: BLE001 -- a service loop: report and keep going
+            self.rejected += 1
+            print(f"[B200Server] request rejected: {type(e).__name__}: {e}", flush=True)
+            return self._empty_answer()
 
     def start(self, max_requests: Optional[int] = None):
         """Accept one connection and serve it until the client closes it (or max_requests have been answered)."""

@@ -1065,6 +1065,17 @@ int b200_ivfpq_merge_shards_peer(int nshard, int64_t nq, int k, const void* cons
     return 0;
 }
 
+int b200_ivfpq_segment_sums(int64_t k, int d, const float* d_x, const int64_t* d_order, const int64_t* d_start,
+                            float* d_sums, void* stream) {
+    if (k < 0 || d <= 0) return fail(B200_IVFPQ_EINVAL, "bad k / d");
+    if (k == 0) return 0;
+    if (!d_x || !d_order || !d_start || !d_sums) return fail(B200_IVFPQ_EINVAL, "null pointer");
+    if (k >= (int64_t(1) << 31)) return fail(B200_IVFPQ_EINVAL, "k too large");
+    segment_sums_kernel<<<(unsigned)k, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_order, d_start, d, d_sums);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int b200_ivfpq_set_stage_timing(b200_ivfpq_t h, int enable) {
     if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
     h->timing = enable != 0;

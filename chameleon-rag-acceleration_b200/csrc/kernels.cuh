@@ -717,4 +717,23 @@ __global__ void __launch_bounds__(kThreads) encode_kernel(const float* __restric
     codes[i * M + m] = static_cast<uint8_t>(arg);
 }
 
+// ------------------------------------------------------------------------------------------------
+// a10 (train): the centroid update of Lloyd's iteration as a DETERMINISTIC segmented sum.  Rows are visited in
+// the order given (a stable sort of the assignment), one CTA per centroid, one column per thread, sequential fp32
+// adds: the same training set and seeds give the same codebooks bit for bit on every run (an atomic scatter-add does
+// not, and the bench lines of different runs / GPU counts would then come from different indexes).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) segment_sums_kernel(const float* __restrict__ x,
+                                                                const int64_t* __restrict__ order,
+                                                                const int64_t* __restrict__ start, int d,
+                                                                float* __restrict__ sums) {
+    const int64_t c = blockIdx.x;
+    const int64_t beg = start[c], end = start[c + 1];
+    for (int j = threadIdx.x; j < d; j += kThreads) {
+        float a = 0.0f;
+        for (int64_t i = beg; i < end; i++) a = __fadd_rn(a, __ldg(x + order[i] * d + j));
+        sums[c * d + j] = a;
+    }
+}
+
 }  // namespace b200

@@ -107,6 +107,13 @@ B200_API int b200_ivfpq_search_host(b200_ivfpq_t h, int64_t nq, const float* h_x
 B200_API int b200_ivfpq_assign_encode(b200_ivfpq_t h, int64_t n, const float* d_x, int64_t* d_list_no, uint8_t* d_codes,
                              void* stream);
 
+/* a10 -- the centroid update of index.train's Lloyd iterations (bench_cpu_performance.py:98-109, bench_gpu_1bn.py:
+ * 522-542): d_sums[c] = sum of the rows d_x[d_order[i]] for i in [d_start[c], d_start[c+1]), added one after the other
+ * in that order (fp32), so that training is reproducible bit for bit.  d_x is (n, d) f32, d_order i64, d_start (k+1)
+ * i64, d_sums (k, d) f32. */
+B200_API int b200_ivfpq_segment_sums(int64_t k, int d, const float* d_x, const int64_t* d_order, const int64_t* d_start,
+                            float* d_sums, void* stream);
+
 /* multi-GPU merge (K5) -- what Faiss IndexShards does on the host after per-GPU searches
  * (bench_gpu_performance_OSDI.py:587-604; merge semantics bench_multi_cpu_performance_OSDI.py:203-219):
  * d_Ds / d_Is are (nshard, nq, k) as produced by an all-gather of per-shard results; output (nq, k) is the

@@ -166,6 +166,45 @@ def test_faiss_container_roundtrip(oracle, tmp_path):
         parse_faiss_ivfpq(b"IxF2" + bytes(64))
 
 
+def test_faiss_container_bytes_by_hand(tmp_path):
+    """The coarse quantizer's flat storage, byte for byte, built by hand from the Faiss write macros as documented in
+    faiss_io.py: the default writer emits count = nlist * d followed by the raw float32 bytes (WRITEVECTOR /
+    WRITEXBVECTOR on the uint8 image, i.e. what Faiss <= 1.6 and >= 1.7.2 read); the optional 'float' variant emits
+    count = nlist * d / 4 (WRITEXBVECTOR on the float vector); the reader takes both."""
+    import struct
+    from b200ivfpq.faiss_io import parse_faiss_ivfpq, write_faiss_ivfpq
+    nlist, d, M = 4, 8, 2
+    coarse = np.arange(nlist * d, dtype=np.float32).reshape(nlist, d)
+    pq = (np.arange(M * 256 * (d // M), dtype=np.float32) * 0.5).reshape(M, 256, d // M)
+    offsets = np.array([0, 2, 2, 3, 3], np.int64)
+    codes = np.array([[1, 2], [3, 4], [5, 6]], np.uint8)
+    ids = np.array([10, 11, 12], np.int64)
+    a = {"coarse": coarse, "pq": pq, "offsets": offsets, "codes": codes, "ids": ids}
+
+    def by_hand(count):
+        hdr = lambda dd, n: struct.pack("<iqqq?i", dd, n, 1 << 20, 1 << 20, True, 1)
+        out = b"IwPQ" + hdr(d, 3) + struct.pack("<QQ", nlist, 5)
+        out += b"IxF2" + hdr(d, nlist) + struct.pack("<Q", count) + coarse.tobytes()
+        out += struct.pack("<bQ", 0, 0) + struct.pack("<?Q", True, M)
+        out += struct.pack("<QQQQ", d, M, 8, pq.size) + pq.tobytes()
+        out += b"ilar" + struct.pack("<QQ", nlist, M)
+        out += b"sprs" + struct.pack("<Q", 4) + struct.pack("<QQQQ", 0, 2, 2, 1)
+        out += codes[0:2].tobytes() + ids[0:2].tobytes() + codes[2:3].tobytes() + ids[2:3].tobytes()
+        return out
+
+    for storage, count in (("bytes", nlist * d), ("float", nlist * d // 4)):
+        fn = os.path.join(tmp_path, f"hand_{storage}.index")
+        write_faiss_ivfpq(fn, a, nprobe=5, flat_storage=storage)
+        assert open(fn, "rb").read() == by_hand(count), storage
+        z = parse_faiss_ivfpq(by_hand(count))
+        for key in ("coarse", "pq", "offsets", "codes", "ids"):
+            _util.assert_bit_equal(z[key], a[key], key)
+    # the default is the count every current Faiss release reads
+    fn = os.path.join(tmp_path, "default.index")
+    write_faiss_ivfpq(fn, a, nprobe=5)
+    assert open(fn, "rb").read() == by_hand(nlist * d)
+
+
 def test_sass_is_blackwell_native_and_exact():
     """Static evidence from the built library (cuobjdump, no GPU needed): the coarse GEMM uses tcgen05 / TMEM / TMA,
     the two-query scan uses LDS.64 + FFMA2, and no kernel on the exact-arithmetic path contains a contracted
@@ -312,8 +351,18 @@ def test_ground_truth_heap_and_helpers():
             unsupported(None, 8, 4)
 
 
+def test_clustering_has_no_cpu_path():
+    import torch
+    import b200ivfpq as faiss
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        faiss.Clustering(6, 4).train(np.zeros((64, 6), np.float32))
+
+
+@pytest.mark.gpu
 def test_clustering_wrapper_trains_centroids():
-    """faiss.Clustering(d, k).train(x, index) as bench_gpu_1bn.py:520-542 calls it (runs on the CPU when there is no GPU)."""
+    """faiss.Clustering(d, k).train(x, index) as bench_gpu_1bn.py:520-542 calls it."""
     import torch
     import b200ivfpq as faiss
     rng = np.random.default_rng(1)
@@ -337,6 +386,24 @@ def test_clustering_wrapper_trains_centroids():
     # every true centre has a learned centroid next to it
     d2 = ((centres[:, None, :] - c[None, :, :]) ** 2).sum(2)
     assert (d2.min(axis=1) < 0.05).all(), d2.min(axis=1)
+
+
+@pytest.mark.gpu
+def test_training_is_reproducible():
+    """Same training set and seeds -> the same codebooks bit for bit (the centroid update is a sequential segmented sum,
+    not an atomic scatter-add): bench lines of different runs and GPU counts come from the same index."""
+    import torch
+    import b200ivfpq as faiss
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    x = torch.randn((60000, 32), generator=g, device="cuda")
+    books = []
+    for _ in range(2):
+        index = faiss.index_factory(32, "IVF256,PQ8")
+        index.cp_niter = 6
+        index.train(x)
+        books.append((index.quantizer.xb_tensor().clone(), index.pq.centroids_tensor().clone()))
+    assert torch.equal(books[0][0], books[1][0]) and torch.equal(books[0][1], books[1][1])
 
 
 def test_vector_transform_persistence(tmp_path, monkeypatch):

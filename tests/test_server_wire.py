@@ -77,6 +77,35 @@ def test_server_round_trips(with_lists):
     srv.close()
 
 
+def test_server_survives_a_bad_request():
+    """A request with another k is rejected BEFORE any search runs, answered with an empty result of the agreed length,
+    and the loop keeps serving (the reference's server does not die on a bad request)."""
+    import threading
+    from b200ivfpq.server import B200Client, B200Server
+    index = _FakeIndex()
+    calls = []
+    orig = index.search
+    index.search = lambda x, k: (calls.append(k), orig(x, k))[1]
+    srv = B200Server(index, port=0, batch_size=4, dim=index.d, default_k=5, nprobe=3)
+    port = srv.server.getsockname()[1]
+    t = threading.Thread(target=srv.start, kwargs={"max_requests": 2}, daemon=True)
+    t.start()
+    bad = B200Client("127.0.0.1", port, 4, index.d, k=7)
+    bad.k = 7
+    q = np.random.default_rng(0).random((4, index.d), dtype=np.float32)
+    from b200ivfpq import server as w
+    bad.sock.sendall(w.encode_request(q, 7)[:srv.query_msg_len])          # k = 7 in the header, same message length
+    ans = w._recv_exact(bad.sock, w.answer_message_len(5, 4))
+    I, D = w.decode_answer(ans, 5, 4)
+    assert (I == -1).all() and calls == [], "a rejected request must not reach the index"
+    bad.k = 5
+    out = bad.retrieve(q)
+    assert out["id"].shape == (4, 5) and calls == [5] and srv.rejected == 1
+    bad.close()
+    t.join(timeout=5)
+    srv.close()
+
+
 @pytest.mark.gpu
 def test_server_with_a_real_index(oracle):
     import _util
