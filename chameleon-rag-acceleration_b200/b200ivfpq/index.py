@@ -511,6 +511,39 @@ class IndexIVFPQ:
             return D, I
         return D.cpu().numpy(), I.cpu().numpy()
 
+    def search_preassigned_begin(self, x: torch.Tensor, k: int, list_ids: torch.Tensor, boot_lo: int, boot_hi: int):
+        """First half of a sharded search (b200_ivfpq_search_preassigned_begin): returns the (nq,) int32 tensor of
+        bootstrap-threshold bits (valid for the queries [boot_lo, boot_hi), +inf bits elsewhere), or None when the
+        streaming pipeline does not apply to this shape."""
+        dev = self._device()
+        nq, nprobe = x.shape[0], int(list_ids.shape[1])
+        self._check_search(k, nprobe)
+        h = self._sync_lists()
+        thr = torch.empty(nq, dtype=torch.int32, device=dev)
+        self._split_keep = (x.contiguous(), list_ids.to(dev, torch.int64).contiguous())   # alive until _finish
+        with torch.cuda.device(dev):
+            rc = h.lib.b200_ivfpq_search_preassigned_begin(h.h, nq, self._split_keep[0].data_ptr(), k, nprobe,
+                                                           self._split_keep[1].data_ptr(), int(boot_lo), int(boot_hi),
+                                                           thr.data_ptr(), _stream_ptr(dev))
+        if rc == 5:         # B200_IVFPQ_EUNSUPPORTED
+            self._split_keep = None
+            return None
+        _lib.check(rc)
+        return thr
+
+    def search_preassigned_finish(self, thr: torch.Tensor, nq: int, k: int, out=None):
+        dev = self._device()
+        h = self._ensure_handle()
+        if out is not None:
+            D, I = _check_out(out, nq, k, dev)
+        else:
+            D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(h.lib.b200_ivfpq_search_preassigned_finish(h.h, thr.data_ptr(), D.data_ptr(), I.data_ptr()))
+        self._split_keep = None
+        return D, I
+
     # ------------------------------------------------------------------ instrumentation (bench.py)
     def set_stage_timing(self, enable: bool):
         h = self._ensure_handle()

@@ -261,6 +261,8 @@ class DistributedIndexIVFPQ:
         if peer_merge is None:
             peer_merge = os.environ.get("B200_IVFPQ_P2P", "1") != "0"
         self.peer_merge = bool(peer_merge) and merge_fn is None and local_search_fn is None and self.world > 1
+        self.exchange_thresholds = (os.environ.get("B200_IVFPQ_THR_EXCHANGE", "1") != "0" and local_search_fn is None
+                                    and merge_fn is None)
         self._symm = None          # (buffer, handle, capacity in result slots)
         self._readers_pending = False   # peers may still be reading my buffer (previous search's merge)
         self.peer_merge_error = None
@@ -294,6 +296,14 @@ class DistributedIndexIVFPQ:
             _, probes = self.local.quantizer.search(xq, min(nprobe, self.local.nlist))
         if self.shard_mode == "list":
             probes = torch.where(probes % self.world == self.rank, probes, torch.full_like(probes, -1))
+        if sliced and self.shard_mode == "vector" and self.exchange_thresholds and \
+                hasattr(self.local, "search_preassigned_begin"):
+            # every rank bootstraps the filter thresholds of ITS slice of the queries on its own shard (any shard's k-th
+            # best distance bounds the global one); one all-reduce MIN of nq x 4 bytes gives every rank all of them
+            thr = self.local.search_preassigned_begin(xq, k, probes, bounds[self.rank], bounds[self.rank + 1])
+            if thr is not None:
+                self.dist.all_reduce(thr, op=self.dist.ReduceOp.MIN, group=self.group)
+                return self.local.search_preassigned_finish(thr, nq, k, out=out)
         if out is not None:
             return self.local.search_preassigned(xq, k, probes, out=out)
         return self.local.search_preassigned(xq, k, probes)

@@ -112,6 +112,16 @@ struct b200_ivfpq_index {
     DevBuf ql_mu, ql_snorm, ql_sbmin, ql_sbstep, ql_lut, ql_scale, ql_amin, ql_counters;
     // streaming pipeline (scan_stream.cuh)
     DevBuf st_srec, st_sfill, st_ctr, st_slab, st_qcnt, st_qflag, st_qkey, st_prefix, st_pdis;
+    // a search split in two for the multi-GPU threshold exchange (b200_ivfpq_search_preassigned_begin / _finish)
+    struct Pending {
+        bool valid = false;
+        ScanParams sp;
+        QlHostParams qp;
+        StHostBuffers sb;
+        int64_t nq = 0;
+        int k = 0, nprobe = 0, st_ctas = 0, ql_ctas = 0;
+        cudaStream_t st = nullptr;
+    } pend;
     int st_mode = 1;            // B200_IVFPQ_STREAM=0: in-kernel top-k (scan_qlut_kernel) instead of the streaming pipeline
     double st_rate = 0.01;      // B200_IVFPQ_STREAM_RATE: survivor records provisioned per (query, code) pair
     int st_capq = 0;            // B200_IVFPQ_STREAM_CAPQ: keys per query slab (0 = max(1024, 32 k))
@@ -378,8 +388,15 @@ int ql_prepare(b200_ivfpq_index* h, cudaStream_t st) {
     return 0;
 }
 
+// split = nullptr: the whole search.  split != nullptr (b200_ivfpq_search_preassigned_begin): everything up to the
+// bootstrap thresholds of the queries [split->lo, split->hi); the rest is enqueued by search_finish.
+struct SplitArgs {
+    int64_t lo, hi;
+    uint32_t* d_thr_out;   // (nq) the thresholds of [lo, hi) are written here, +inf bits elsewhere
+};
+
 int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int nprobe, const int64_t* d_list_ids,
-                float* d_D, int64_t* d_I, cudaStream_t st) {
+                float* d_D, int64_t* d_I, cudaStream_t st, const SplitArgs* split = nullptr) {
     if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
     if (!h->cent || !h->pq) return fail(B200_IVFPQ_ESTATE, "index is not trained (set_codebooks not called)");
     if (!h->has_lists) return fail(B200_IVFPQ_ESTATE, "inverted lists not set (set_lists not called)");
@@ -388,8 +405,9 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     if (nprobe < 1 || nprobe > B200_IVFPQ_MAX_NPROBE)
         return fail(B200_IVFPQ_EINVAL, "nprobe = %d out of [1, %d]", nprobe, B200_IVFPQ_MAX_NPROBE);
     if (nq == 0) return 0;
-    if (!d_xq || !d_D || !d_I) return fail(B200_IVFPQ_EINVAL, "null query / result pointer");
+    if (!d_xq || (!split && (!d_D || !d_I))) return fail(B200_IVFPQ_EINVAL, "null query / result pointer");
     CUDA_TRY(cudaSetDevice(h->device));
+    h->pend.valid = false;
     if (!d_list_ids && nprobe > h->nlist) nprobe = static_cast<int>(h->nlist);   // Faiss clamps nprobe to nlist
 
     const bool legacy = h->scan_variant == 6;   // B200_IVFPQ_SCAN=legacy: round 1's kernel selection (no scan_qlut)
@@ -405,6 +423,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
     if (!d_list_ids) qb = std::min<int64_t>(qb, coarse_chunk(h));
     qb = std::min<int64_t>(qb, std::max<int64_t>(1, (int64_t)(kPairOutBudget / (sizeof(uint64_t) * (size_t)nprobe * k))));
     qb = std::min<int64_t>(qb, (int64_t)((1ll << 30) / nprobe));
+    if (split && qb < nq) return fail(B200_IVFPQ_EUNSUPPORTED, "split search: the batch does not fit one query chunk");
     if (timing) {
         int rc0 = ensure_events(h, (size_t)((nq + qb - 1) / qb));
         if (rc0) return rc0;
@@ -511,6 +530,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
                 CUDA_TRY(cudaMemsetAsync(h->ql_counters.p, 0, 3 * sizeof(unsigned long long), st));
             }
         }
+        if (split && !ql_ctas) return fail(B200_IVFPQ_EUNSUPPORTED, "split search: the per-query-table scan does not apply here");
         const int gsz = (quad_ctas || ql_ctas) ? 4 : 2;
         if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * quad_scratch_float4(h->M) * quad_ctas))) return rc;
 
@@ -621,6 +641,28 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             qp.counters = h->ql_stats ? h->ql_counters.as<unsigned long long>() : nullptr;
             qp.guard = nullptr;
             qp.qflag = nullptr;
+            if (split) {
+                if (!st_ctas) return fail(B200_IVFPQ_EUNSUPPORTED, "split search: the streaming pipeline does not apply here");
+                if (st_launch_boot(sp, qp, sb, nqc, split->lo, split->hi, st))
+                    return fail(B200_IVFPQ_ECUDA, "bootstrap launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                g_launches.fetch_add(1);
+                CUDA_TRY(cudaMemcpyAsync(split->d_thr_out, sp.qthr, sizeof(uint32_t) * nqc, cudaMemcpyDeviceToDevice, st));
+                h->pend.valid = true;
+                h->pend.sp = sp;
+                h->pend.qp = qp;
+                h->pend.sb = sb;
+                h->pend.nq = nqc;
+                h->pend.k = k;
+                h->pend.nprobe = nprobe;
+                h->pend.st_ctas = st_ctas;
+                h->pend.ql_ctas = ql_ctas;
+                h->pend.st = st;
+                if (tm) {
+                    CUDA_TRY(cudaEventRecord(h->ev[4], st));
+                    CUDA_TRY(cudaEventRecord(h->ev[5], st));
+                }
+                return 0;
+            }
             if (st_ctas) {
                 // streaming pipeline: thresholds -> filter -> exact evaluation -> select; D / I are final after it ...
                 if (tm) h->filter_timed = true;
@@ -900,6 +942,43 @@ int b200_ivfpq_search_preassigned(b200_ivfpq_t h, int64_t nq, const float* d_xq,
 
 namespace {
 
+int search_finish(b200_ivfpq_index* h, const uint32_t* d_thr_in, float* d_D, int64_t* d_I) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (!h->pend.valid) return fail(B200_IVFPQ_ESTATE, "search_preassigned_finish without a pending _begin");
+    if (!d_D || !d_I) return fail(B200_IVFPQ_EINVAL, "null result pointer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    auto& pe = h->pend;
+    pe.valid = false;
+    cudaStream_t st = pe.st;
+    const bool tm = h->timing && h->ev != nullptr;
+    if (tm) h->filter_timed = true;
+    if (tm) CUDA_TRY(cudaEventRecord(h->ev[3], st));   // the exchange sits between pair set-up and scan
+    if (st_launch_rest(pe.sp, pe.qp, pe.sb, pe.nq, h->ids, d_D, d_I, pe.st_ctas, h->num_sms, st, tm ? h->ev[6] : nullptr,
+                       tm ? h->ev[7] : nullptr, d_thr_in))
+        return fail(B200_IVFPQ_ECUDA, "streaming scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(3 + (d_thr_in ? 1 : 0));
+    QlHostParams qp = pe.qp;
+    qp.guard = st_overflow_flag(pe.sb.ctr);
+    qp.qflag = static_cast<const int*>(pe.sb.qflag);
+    if (ql_launch_scan(pe.sp, qp, pe.ql_ctas, st))
+        return fail(B200_IVFPQ_ECUDA, "per-query-table scan launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1);
+    if (tm) CUDA_TRY(cudaEventRecord(h->ev[4], st));
+    size_t msmem = TopK::smem_bytes(pe.k, kMergeCap);
+    int rc;
+    if ((rc = set_smem(merge_query_kernel, msmem))) return rc;
+    merge_query_kernel<<<(unsigned)pe.nq, kThreads, msmem, st>>>(h->out_keys.as<uint64_t>(), h->out_cnt.as<int>(), pe.sp.probe,
+                                                                h->offsets.as<int64_t>(), h->ids, pe.nprobe, pe.k, 1,
+                                                                h->qthr.as<uint32_t>(), d_D, d_I, qp.guard, qp.qflag);
+    LAUNCH_CHECK();
+    if (tm) {
+        CUDA_TRY(cudaEventRecord(h->ev[5], st));
+        h->timed_chunks = 1;
+        h->stage_valid = true;
+    }
+    return 0;
+}
+
 constexpr int64_t kGraphMaxNq = 64;
 
 uint64_t graph_epoch(const b200_ivfpq_index* h) { return (h->state_epoch << 32) ^ g_ws_epoch.load(); }
@@ -978,6 +1057,20 @@ int search_host_small(b200_ivfpq_index* h, int64_t nq, const float* h_xq, int k,
 }
 
 }  // namespace
+
+extern "C" int b200_ivfpq_search_preassigned_begin(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe,
+                                                   const int64_t* d_list_ids, int64_t boot_lo, int64_t boot_hi,
+                                                   uint32_t* d_thr_out, void* stream) {
+    if (!d_list_ids || !d_thr_out) return fail(B200_IVFPQ_EINVAL, "null list ids / threshold buffer");
+    if (boot_lo < 0 || boot_hi < boot_lo || boot_hi > nq) return fail(B200_IVFPQ_EINVAL, "bad bootstrap slice");
+    if (nq <= 0) return fail(B200_IVFPQ_EINVAL, "nq <= 0");
+    SplitArgs sa{boot_lo, boot_hi, d_thr_out};
+    return search_impl(h, nq, d_xq, k, nprobe, d_list_ids, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream), &sa);
+}
+
+extern "C" int b200_ivfpq_search_preassigned_finish(b200_ivfpq_t h, const uint32_t* d_thr_in, float* d_D, int64_t* d_I) {
+    return search_finish(h, d_thr_in, d_D, d_I);
+}
 
 extern "C" int b200_ivfpq_search_host(b200_ivfpq_t h, int64_t nq, const float* h_xq, int k, int nprobe, float* h_D,
                                       int64_t* h_I) {

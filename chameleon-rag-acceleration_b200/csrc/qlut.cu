@@ -160,8 +160,8 @@ int st_filter_grid_t(int64_t npairs, int num_sms) {
 }
 
 template <int M>
-int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
-                cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+int st_boot_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int64_t lo, int64_t hi,
+              cudaStream_t st) {
     if (sp.k <= 128 && getenv("B200_IVFPQ_BOOT_BLOCK") == nullptr) {
         // warp-level bootstrap: W winners per warp, 8 W >= 2 k exact candidates
         const int W = sp.k <= 32 ? 8 : sp.k <= 64 ? 16 : 32;
@@ -173,7 +173,7 @@ int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, i
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm) != cudaSuccess)      \
             return -1;                                                                                               \
         kernel<<<(unsigned)nq, kStBootThreads, bsm, st>>>(sp.xq, sp.cent, sp.pq, sp.offsets, sp.codes, sp.probe,     \
-                                                          sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr);         \
+                                                          sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr, lo, hi); \
     }
         if (W == 8) ST_BOOTW(8) else if (W == 16) ST_BOOTW(16) else ST_BOOTW(32)
 #undef ST_BOOTW
@@ -183,9 +183,14 @@ int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, i
             cudaFuncSetAttribute(st_boot_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm) != cudaSuccess)
             return -1;
         st_boot_kernel<M><<<(unsigned)nq, kStBootThreads, bsm, st>>>(sp.xq, sp.cent, sp.pq, sp.offsets, sp.codes, sp.probe,
-                                                                     sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr);
+                                                                     sp.nprobe, sp.d, sp.dsub, sp.k, ql, stp, sp.qthr, lo, hi);
     }
-    if (cudaPeekAtLastError() != cudaSuccess) return -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+template <int M>
+int st_rest_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
+              cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     const size_t fsm = st_filter_smem<M>();
     if (cudaFuncSetAttribute(st_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
     if (ev0 && cudaEventRecord(ev0, st) != cudaSuccess) return -1;
@@ -202,20 +207,8 @@ int st_launch_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, i
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
-}  // namespace
-
-int st_filter_grid(int M, int64_t npairs, int num_sms) {
-    switch (M) {
-        case 16: return st_filter_grid_t<16>(npairs, num_sms);
-        case 32: return st_filter_grid_t<32>(npairs, num_sms);
-        case 64: return st_filter_grid_t<64>(npairs, num_sms);
-        default: return 0;
-    }
-}
-
-int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,
-              int64_t* I, int filter_grid, int num_sms, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
-    QlParams ql;
+void st_fill(const QlHostParams& qp, const StHostBuffers& sb, const int64_t* ids, float* D, int64_t* I, QlParams& ql,
+             StParams& stp) {
     ql.snorm = qp.snorm;
     ql.sbmin = qp.sbmin;
     ql.sbstep = qp.sbstep;
@@ -226,7 +219,6 @@ int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers&
     ql.counters = nullptr;
     ql.guard = nullptr;
     ql.qflag = nullptr;
-    StParams stp;
     stp.srec = static_cast<uint2*>(sb.srec);
     stp.sfill = static_cast<unsigned int*>(sb.sfill);
     stp.max_chunks = sb.max_chunks;
@@ -245,13 +237,55 @@ int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers&
     }
     stp.D = D;
     stp.I = I;
+}
+
+}  // namespace
+
+int st_filter_grid(int M, int64_t npairs, int num_sms) {
+    switch (M) {
+        case 16: return st_filter_grid_t<16>(npairs, num_sms);
+        case 32: return st_filter_grid_t<32>(npairs, num_sms);
+        case 64: return st_filter_grid_t<64>(npairs, num_sms);
+        default: return 0;
+    }
+}
+
+int st_launch_boot(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, int64_t lo, int64_t hi,
+                   cudaStream_t st) {
+    QlParams ql;
+    StParams stp;
+    st_fill(qp, sb, nullptr, nullptr, nullptr, ql, stp);
     if (cudaMemsetAsync(sb.ctr, 0, kStCtrBytes, st) != cudaSuccess) return -1;
     switch (sp.M) {
-        case 16: return st_launch_t<16>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
-        case 32: return st_launch_t<32>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
-        case 64: return st_launch_t<64>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
+        case 16: return st_boot_t<16>(sp, ql, stp, nq, lo, hi, st);
+        case 32: return st_boot_t<32>(sp, ql, stp, nq, lo, hi, st);
+        case 64: return st_boot_t<64>(sp, ql, stp, nq, lo, hi, st);
         default: return -1;
     }
+}
+
+int st_launch_rest(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids,
+                   float* D, int64_t* I, int filter_grid, int num_sms, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1,
+                   const uint32_t* thr_in) {
+    QlParams ql;
+    StParams stp;
+    st_fill(qp, sb, ids, D, I, ql, stp);
+    if (thr_in) {
+        st_apply_thresholds_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(thr_in, nq, sp.qthr, stp.qkey);
+        if (cudaPeekAtLastError() != cudaSuccess) return -1;
+    }
+    switch (sp.M) {
+        case 16: return st_rest_t<16>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
+        case 32: return st_rest_t<32>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
+        case 64: return st_rest_t<64>(sp, ql, stp, nq, filter_grid, num_sms, st, ev0, ev1);
+        default: return -1;
+    }
+}
+
+int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,
+              int64_t* I, int filter_grid, int num_sms, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+    if (st_launch_boot(sp, qp, sb, nq, 0, nq, st)) return -1;
+    return st_launch_rest(sp, qp, sb, nq, ids, D, I, filter_grid, num_sms, st, ev0, ev1, nullptr);
 }
 
 }  // namespace b200

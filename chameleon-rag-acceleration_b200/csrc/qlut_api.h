@@ -70,5 +70,13 @@ int st_filter_grid(int M, int64_t npairs, int num_sms);        // 0: does not fi
 int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,
               int64_t* I, int filter_grid, int num_sms, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 const int* st_overflow_flag(const void* ctr);
+// the same pipeline in two halves, for the multi-GPU threshold exchange: boot bootstraps the thresholds of the queries
+// [lo, hi) only (scan positions and coarse distances of all of them); rest takes thr_in (nq distance bits, or nullptr)
+// -- e.g. the all-reduce MIN over the ranks of every rank's qthr -- before filter / evaluation / select
+int st_launch_boot(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, int64_t lo, int64_t hi,
+                   cudaStream_t st);
+int st_launch_rest(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids,
+                   float* D, int64_t* I, int filter_grid, int num_sms, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1,
+                   const uint32_t* thr_in);
 
 }  // namespace b200

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kStBootThreads)
 st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, const float* __restrict__ pq,
                const int64_t* __restrict__ offsets, const uint8_t* __restrict__ codes,
                const int32_t* __restrict__ probe, int nprobe, int d, int dsub, int k, QlParams ql, StParams st,
-               uint32_t* __restrict__ qthr) {
+               uint32_t* __restrict__ qthr, int64_t boot_lo, int64_t boot_hi) {
     extern __shared__ __align__(16) unsigned char smem_boot[];
     const int dpad = (d + 3) & ~3;
     float* qv = reinterpret_cast<float*>(smem_boot);
@@ -192,6 +192,15 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
         if (lane == 0) st.pdis[q * nprobe + r] = a;
     }
     __syncthreads();
+    if (q < boot_lo || q >= boot_hi) {
+        // multi-GPU: another rank bootstraps this query's threshold on ITS shard (any shard's k-th best distance bounds
+        // the global one); the thresholds are exchanged before the filter runs (st_apply_thresholds_kernel)
+        if (tid == 0) {
+            qthr[q] = kInfBits;
+            st.qkey[q] = kPadKey;
+        }
+        return;
+    }
     // candidates: the first codes in scan order, ranked by the estimated distance dis0 + SB + sum_m A; all of them
     // go to the queue (it holds kStBootCodes keys), one fold at the end
     const uint32_t ncand = static_cast<uint32_t>(s_total < static_cast<unsigned long long>(st.boot_codes) ? s_total : st.boot_codes);
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(kStBootThreads)
 st_boot_warp_kernel(const float* __restrict__ xq, const float* __restrict__ cent, const float* __restrict__ pq,
                     const int64_t* __restrict__ offsets, const uint8_t* __restrict__ codes,
                     const int32_t* __restrict__ probe, int nprobe, int d, int dsub, int k, QlParams ql, StParams st,
-                    uint32_t* __restrict__ qthr) {
+                    uint32_t* __restrict__ qthr, int64_t boot_lo, int64_t boot_hi) {
     static_assert(M % 16 == 0, "16 lanes per candidate, M / 16 sub-quantizers per lane");
     extern __shared__ __align__(16) unsigned char smem_boot[];
     const int dpad = (d + 3) & ~3;
@@ -372,6 +381,13 @@ st_boot_warp_kernel(const float* __restrict__ xq, const float* __restrict__ cent
         if (lane == 0) st.pdis[q * nprobe + r] = a;
     }
     __syncthreads();
+    if (q < boot_lo || q >= boot_hi) {   // see st_boot_kernel
+        if (tid == 0) {
+            qthr[q] = kInfBits;
+            st.qkey[q] = kPadKey;
+        }
+        return;
+    }
     const uint32_t ncand = static_cast<uint32_t>(s_total < static_cast<unsigned long long>(st.boot_codes) ? s_total : st.boot_codes);
     const float sq = ql.qscale[q], aq = ql.qamin[q];
     const float inv = sq > 0.0f ? 1.0f / sq : 0.0f;
@@ -508,6 +524,19 @@ st_boot_warp_kernel(const float* __restrict__ xq, const float* __restrict__ cent
             qthr[q] = t;
             st.qkey[q] = tkey;
         }
+    }
+}
+
+// Multi-GPU threshold exchange: thr_in[q] = the smallest bootstrap threshold any rank found for query q (all-reduce MIN
+// of the distance bits).  Thresholds that came from another shard admit by distance only (tag = all ones).
+__global__ void st_apply_thresholds_kernel(const uint32_t* __restrict__ thr_in, int64_t nq, uint32_t* __restrict__ qthr,
+                                           uint64_t* __restrict__ qkey) {
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t t = thr_in[q];
+    if (t < qthr[q]) {
+        qthr[q] = t;
+        qkey[q] = (static_cast<uint64_t>(t) << 32) | 0xffffffffull;
     }
 }
 

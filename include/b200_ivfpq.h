@@ -95,6 +95,18 @@ B200_API int b200_ivfpq_search(b200_ivfpq_t h, int64_t nq, const float* d_xq, in
 B200_API int b200_ivfpq_search_preassigned(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe,
                                   const int64_t* d_list_ids, float* d_D, int64_t* d_I, void* stream);
 
+/* The same search in two halves, for an index sharded by vector over several GPUs (bench_gpu_performance_OSDI.py:586-604,
+ * co.shard = True).  Every shard needs, per query, an upper bound on the FINAL k-th distance before it filters its codes;
+ * any shard's own k-th best distance is one.  _begin does everything up to those bootstrap thresholds, but only for the
+ * queries [boot_lo, boot_hi) (d_thr_out, nq x u32 distance bits, +inf bits elsewhere); the caller combines the ranks'
+ * arrays (an all-reduce MIN of nq x 4 bytes over NVLink) and hands the result to _finish, which filters, evaluates and
+ * selects on the stream given to _begin.  One pending search per handle; B200_IVFPQ_EUNSUPPORTED when the streaming
+ * pipeline does not apply to this shape (use b200_ivfpq_search_preassigned then). */
+B200_API int b200_ivfpq_search_preassigned_begin(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe,
+                                        const int64_t* d_list_ids, int64_t boot_lo, int64_t boot_hi,
+                                        uint32_t* d_thr_out, void* stream);
+B200_API int b200_ivfpq_search_preassigned_finish(b200_ivfpq_t h, const uint32_t* d_thr_in, float* d_D, int64_t* d_I);
+
 /* Same call with HOST buffers (numpy arrays, the reference's convention: faiss_retriever.py:227-275):
  * H2D of the queries, search, D2H of the results, synchronised.  This is the end-to-end path bench.py
  * reports as e2e. */

@@ -126,6 +126,87 @@ class _OracleShard:
         return torch.from_numpy(D), torch.from_numpy(I)
 
 
+class _OracleShardSplit(_OracleShard):
+    """The same stand-in with the two-half search of the threshold exchange (IndexIVFPQ.search_preassigned_begin /
+    _finish): begin answers the k-th best LOCAL distance of the queries in its slice (+inf bits elsewhere), finish drops
+    every local result above the exchanged threshold -- what the CUDA filter does with it."""
+
+    def search_preassigned_begin(self, x, k, probes, lo, hi):
+        self._x, self._k, self._probes = x, k, probes
+        thr = torch.full((x.shape[0],), 0x7f800000, dtype=torch.int32)
+        D, _ = self.oracle.C.search_preassigned(x[lo:hi].numpy(), self.a["coarse"], self.a["pq"], self.off, self.codes,
+                                                self.ids, probes[lo:hi].numpy(), k)
+        kth = torch.from_numpy(np.ascontiguousarray(D[:, k - 1])).view(torch.int32)
+        full = torch.from_numpy(D[:, k - 1] < 3e38)                    # fewer than k local results: no threshold
+        thr[lo:hi] = torch.where(full, kth, thr[lo:hi])
+        self.begun = (lo, hi)
+        return thr
+
+    def search_preassigned_finish(self, thr, nq, k, out=None):
+        self.exchanged = thr.clone()
+        D, I = self.oracle.C.search_preassigned(self._x.numpy(), self.a["coarse"], self.a["pq"], self.off, self.codes,
+                                                self.ids, self._probes.numpy(), k)
+        t = thr.view(torch.float32).numpy()[:, None]
+        drop = D > t
+        D[drop], I[drop] = np.finfo(np.float32).max, -1
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def _worker_threshold_exchange(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "chameleon-rag-acceleration_b200"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    from oracle import ivfpq_oracle as oracle
+    from b200ivfpq.shards import DistributedIndexIVFPQ
+    import _util as U
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a = U.make_index_arrays(oracle, 23, 32, 16, 8, 4000, id_scramble=False)
+        xq = torch.from_numpy(U.make_queries(9, a, 40))
+        nprobe, k, nlist = 6, 10, 16
+        sizes = np.diff(a["offsets"])
+        list_no = np.repeat(np.arange(nlist), sizes)
+        keep = (a["ids"] % world) == rank
+        off = np.zeros(nlist + 1, np.int64)
+        off[1:] = np.cumsum(np.bincount(list_no[keep], minlength=nlist))
+        local = _OracleShardSplit(oracle, a, off, a["codes"][keep], a["ids"][keep], nprobe)
+
+        def merge(Ds, Is):
+            D, I = oracle.C.merge_shards(Ds.numpy(), Is.numpy())
+            return torch.from_numpy(D), torch.from_numpy(I)
+
+        index = DistributedIndexIVFPQ(local, merge_fn=merge)
+        index.exchange_thresholds = True            # (off by default for injected merges: this test IS the exchange)
+        D, I = index.search(xq, k)
+        lo, hi = local.begun
+        assert (lo, hi) == ((40 * rank) // world, (40 * (rank + 1)) // world)
+        ex = local.exchanged.view(torch.float32)
+        assert bool(torch.isfinite(ex).all()), "every query got a threshold from some rank"
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), D=D.numpy(), I=I.numpy(), thr=ex.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 4])
+def test_threshold_exchange_keeps_the_result(oracle, tmp_path, world):
+    """Multi-GPU threshold exchange (shards.py): every rank bootstraps the thresholds of its slice of the queries on its
+    own shard, an all-reduce MIN hands all of them to every rank, every shard drops what lies above -- and the merged
+    result is still the unsharded oracle's, because any shard's k-th best distance bounds the global k-th distance."""
+    port = _free_port()
+    mp.spawn(_worker_threshold_exchange, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a = _util.make_index_arrays(oracle, 23, 32, 16, 8, 4000, id_scramble=False)
+    xq = _util.make_queries(9, a, 40)
+    D, I = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], 6, 10)
+    outs = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    for r in range(world):
+        _util.assert_same_modulo_ties(outs[r]["D"], outs[r]["I"], D, I, f"rank {r}")
+        assert np.array_equal(outs[r]["thr"], outs[0]["thr"]), "all ranks hold the same thresholds"
+        assert (outs[r]["thr"] >= D[:, -1]).all(), "a threshold below the true k-th distance would lose results"
+
+
 def _worker_local_search(rank, world, port, out_dir):
     """vector and list layouts through the REAL _local_search (no local_search_fn injection)."""
     for p in (ROOT, os.path.join(ROOT, "chameleon-rag-acceleration_b200"), os.path.join(ROOT, "tests")):
