@@ -34,7 +34,7 @@ CONFIGS = {
     "c1": (1_000_000, 128, 1024, 16, 16, 10, 10_000),
     "c2": (100_000_000, 128, 8192, 16, 32, 10, 10_000),
     "c3": (1_000_000_000, 96, 65536, 16, 64, 100, 10_000),
-    "c4": (100_000_000, 768, 16384, 64, 32, 10, 1),
+    "c4": (100_000_000, 768, 16384, 64, 32, 10, 128),     # RALM: batch-1 latency is reported beside the 128-query step
     "c5": (100_000_000, 128, 8192, 32, 32, 10, 10_000),
 }
 METRIC = "QPS at recall@10 parity (10k-query batch) + p50 batch-1 latency, 1/2/4/8 B200"
@@ -166,7 +166,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU algorithm (oracle port) on the host cores
 # ---------------------------------------------------------------------------------------------------------
-REF_SHRINK = {"c1": 1, "c2": 8, "c3": 64, "c4": 8, "c5": 8}   # the CPU arm's index is nb / shrink vectors in nlist / shrink lists
+REF_SHRINK = {"c1": 1, "c2": 8, "c3": 64, "c4": 32, "c5": 8}   # the CPU arm's index is nb / shrink vectors in nlist / shrink lists
 
 
 def host_cores():
@@ -643,6 +643,36 @@ def run_ours(args):
             lat.append((time.perf_counter() - t0) * 1e3)
     lat_p50 = float(np.median(lat))
     del q1
+    # ---- the same latency while a decode-like GEMM stream shares the GPU (BASELINE config 4: retrieval interleaved with
+    # LLM decode, ralm_tiktok.py:129-192): a second CUDA stream keeps bf16 GEMMs of a decoder-layer shape in flight
+    lat_decode_p50 = None
+    if args.decode_interleave and world == 1:
+        side = torch.cuda.Stream(device=device)
+        wa = torch.randn((8, 8192), device=device, dtype=torch.bfloat16)        # 8 sequences x hidden 8192
+        wb = torch.randn((8192, 28672), device=device, dtype=torch.bfloat16)    # an MLP up-projection
+        stop = threading.Event()
+
+        def decode_loop():
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(side):
+                while not stop.is_set():
+                    for _ in range(16):
+                        torch.matmul(wa, wb)
+                    side.synchronize()
+
+        th = threading.Thread(target=decode_loop, daemon=True)
+        th.start()
+        time.sleep(0.05)
+        lat2 = []
+        for i in range(220):
+            qi = xq_np[i % nq:i % nq + 1]
+            t0 = time.perf_counter()
+            index.search(qi, k)
+            if i >= 20:
+                lat2.append((time.perf_counter() - t0) * 1e3)
+        stop.set()
+        th.join(timeout=5)
+        lat_decode_p50 = float(np.median(lat2))
 
     # ---- roofline of the dominant kernel --------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -741,7 +771,8 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_qps, "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nq * d * 4,
                     "d2h_bytes_per_step": nq * k * 12},
-            "latency_batch1_ms_p50": lat_p50, "recall_at_10": recall, "stages_ms": stages,
+            "latency_batch1_ms_p50": lat_p50, "latency_batch1_with_decode_stream_ms_p50": lat_decode_p50,
+            "recall_at_10": recall, "stages_ms": stages,
             "scan_ms_per_rank": [round(float(v), 3) for v in allr[:, 0]],
             "scan_gbytes_per_rank": [round(float(v) / 1e9, 2) for v in allr[:, 1]],
             "ms_per_step_per_rank": [round(float(v), 3) for v in allr[:, 2]],
@@ -774,6 +805,8 @@ def parse_args(argv=None):
                     help="queries (from the start of the batch) checked against the oracle and timed on the CPU; 0 = the whole "
                          "batch, or 256 when the index is too large to copy to the host (C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-interleave", action="store_true",
+                    help="also measure the batch-1 latency while a second stream runs decoder-shaped bf16 GEMMs (config c4)")
     ap.add_argument("--replicas", type=int, default=1,
                     help="N > 1: R replica groups of N/R vector shards each, the batch sliced by query between the "
                          "groups (the reference's -R, bench_gpu_performance_OSDI.py:613-626); default 1 = all GPUs shard")

@@ -483,10 +483,11 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if (sv == 4 && quad_ctas == 0)
             return fail(B200_IVFPQ_EUNSUPPORTED, "four-query scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);
         // the per-query-table filter (scan_qlut.cuh) replaces both multi-query kernels wherever lists are shared by
-        // queries: its per-work-item cost is a table copy instead of a table build
+        // queries: its per-work-item cost is a table copy instead of a table build.  For M = 32 / 64 it also replaces
+        // the lane-per-code generic kernel (bank-conflicted 32 / 64 KB tables) at any number of queries per list
         int ql_ctas = 0;
         if (ql_supported_host(h->M, h->d, k) && aligned16 && nseg == 1 && h->max_list < (int64_t)kQlHostMaxList &&
-            (sv == 5 || (sv == 0 && !legacy && 2 * npairs >= h->nlist)))
+            (sv == 5 || (sv == 0 && !legacy && (2 * npairs >= h->nlist || h->M != 16))))
             ql_ctas = ql_grid(h->M, h->d, k, npairs, h->num_sms);
         if (sv == 5 && ql_ctas == 0)
             return fail(B200_IVFPQ_EUNSUPPORTED, "per-query-table scan kernel unsupported for M=%d d=%d k=%d", h->M, h->d, k);

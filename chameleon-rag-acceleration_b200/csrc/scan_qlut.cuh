@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) ql_query_tables_kernel(const float* __res
                                                               float* __restrict__ scale, float* __restrict__ amin) {
     constexpr int QB = 64 / M;
     const float kQ = static_cast<float>(qmax);
-    extern __shared__ float ql_qc[];                 // [QB][d]  q - mu
+    extern __shared__ __align__(16) float ql_qc[];   // [QB][d]  q - mu
     __shared__ float s_B[QB][M], s_scale[QB];
     const int tid = threadIdx.x;
     const int64_t q0 = static_cast<int64_t>(blockIdx.x) * QB;
@@ -287,12 +287,26 @@ __global__ void __launch_bounds__(256) ql_query_tables_kernel(const float* __res
         for (int qb = 0; qb < QB; qb++) acc[qb][0] = acc[qb][1] = 0.0f;
         const float* p0 = pq + (static_cast<int64_t>(m) * 256 + tid) * dsub;
         const float* p1 = p0 + 256 * dsub;
-        for (int j = 0; j < dsub; j++) {
-            const float a = __ldg(p0 + j), b = __ldg(p1 + j);
+        if ((dsub & 3) == 0) {
+            for (int j = 0; j < dsub; j += 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p0 + j));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p1 + j));
 #pragma unroll
-            for (int qb = 0; qb < QB; qb++) {
-                acc[qb][0] = fmaf(ql_qc[qb * d + m * dsub + j], a, acc[qb][0]);
-                acc[qb][1] = fmaf(ql_qc[qb * d + (m + 1) * dsub + j], b, acc[qb][1]);
+                for (int qb = 0; qb < QB; qb++) {
+                    const float4 x = *reinterpret_cast<const float4*>(ql_qc + qb * d + m * dsub + j);
+                    const float4 y = *reinterpret_cast<const float4*>(ql_qc + qb * d + (m + 1) * dsub + j);
+                    acc[qb][0] = fmaf(x.w, a.w, fmaf(x.z, a.z, fmaf(x.y, a.y, fmaf(x.x, a.x, acc[qb][0]))));
+                    acc[qb][1] = fmaf(y.w, b.w, fmaf(y.z, b.z, fmaf(y.y, b.y, fmaf(y.x, b.x, acc[qb][1]))));
+                }
+            }
+        } else {
+            for (int j = 0; j < dsub; j++) {
+                const float a = __ldg(p0 + j), b = __ldg(p1 + j);
+#pragma unroll
+                for (int qb = 0; qb < QB; qb++) {
+                    acc[qb][0] = fmaf(ql_qc[qb * d + m * dsub + j], a, acc[qb][0]);
+                    acc[qb][1] = fmaf(ql_qc[qb * d + (m + 1) * dsub + j], b, acc[qb][1]);
+                }
             }
         }
 #pragma unroll
