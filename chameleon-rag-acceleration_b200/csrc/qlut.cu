@@ -191,9 +191,9 @@ int st_boot_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int
 template <int M>
 int st_rest_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
               cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+    if (ev0 && cudaEventRecord(ev0, st) != cudaSuccess) return -1;
     const size_t fsm = st_filter_smem<M>();
     if (cudaFuncSetAttribute(st_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
-    if (ev0 && cudaEventRecord(ev0, st) != cudaSuccess) return -1;
     st_filter_kernel<M><<<(unsigned)filter_grid, QlCfg<M>::kT, fsm, st>>>(sp, ql, stp);
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
     if (ev1 && cudaEventRecord(ev1, st) != cudaSuccess) return -1;

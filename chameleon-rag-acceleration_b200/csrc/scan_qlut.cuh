@@ -11,8 +11,8 @@
 //        dis0(q, list)        SB (stored vector)             A_q[m][code_m]   (query only)
 //
 // (mu = mean of the coarse centroids, any fixed vector works).  Nothing in it depends on the PAIR except one scalar:
-//   * A_q is built ONCE per query and batch (ql_query_tables_kernel), quantised to 11 / 10 / 9 bits for M = 16 / 32 /
-//     64:  u[m][c] = floor((A[m][c] + B_m) * s_q), B_m >= |A[m][.]| (Cauchy-Schwarz);  a work item only copies the
+//   * A_q is built ONCE per query and batch (ql_query_tables_kernel), quantised to 11 bits (M = 16, 32,
+//     64):  u[m][c] = floor((A[m][c] + B_m) * s_q), B_m >= |A[m][.]| (Cauchy-Schwarz);  a work item only copies the
 //     tables of its queries into shared memory (8 KB per query at M = 16, from L2);
 //   * SB is built ONCE per stored vector when the lists are installed (ql_sb_build_kernel, float64), kept as 16 bits
 //     on a per-list grid, rounded DOWN:  SB >= sbmin[l] + sbstep[l] * v;
@@ -57,7 +57,8 @@ struct QlCfg {
     static constexpr int kChunks = M / 16;                  // 16-byte chunks of a code; one 128-byte table row each
     static constexpr int kPlanes = (kChunks + 1) / 2;       // two chunk rows per 256-byte plane row
     static constexpr int kLutBytes = kPlanes * kQlPlaneBytes;
-    static constexpr uint32_t kQMax = 32767u / M;           // 2047, 1023, 511: M entries sum below 2^15
+    static constexpr uint32_t kQMax = 2047u;                // 11-bit entries: the 16 of a chunk sum below 2^15 in a packed
+                                                            // half-word; chunks are widened to 32 bits before they are added
     static constexpr int kTileBlocks = 1024 / kT;           // blocks of kT codes between survivor checks
 };
 
@@ -462,6 +463,35 @@ __device__ __forceinline__ void ql_copy_group_async(QlGroup* dst, const QlGroup*
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 32), "l"(s + 32) : "memory");
 }
 
+// The four packed lower bounds of all chunks of a code -> four "2^23 + integer" floats.  One chunk: the packed
+// half-words go straight into the float's mantissa (one PRMT each).  Several chunks (M = 32, 64): every chunk's packed
+// sums (< 2^15 each) are widened and added in 32 bits (M * 2047 < 2^23).
+template <int M>
+__device__ __forceinline__ void ql_bounds_as_floats(const char* __restrict__ lutb, const uint4 (&v)[M / 16], bool x8, bool x4,
+                                                    uint32_t bsel, const QlOffsets& offs, float (&f)[4]) {
+    if constexpr (M == 16) {
+        const uint2 lb = ql_block16(lutb, v[0], x8, x4, bsel, offs);
+        f[0] = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7410));
+        f[1] = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7432));
+        f[2] = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7410));
+        f[3] = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7432));
+    } else {
+        uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u;
+#pragma unroll
+        for (int h = 0; h < M / 16; h++) {
+            const uint2 lb = ql_block16(lutb + (h >> 1) * kQlPlaneBytes + (h & 1) * 128, v[h], x8, x4, bsel, offs);
+            s0 += lb.x & 0xffffu;
+            s1 += lb.x >> 16;
+            s2 += lb.y & 0xffffu;
+            s3 += lb.y >> 16;
+        }
+        f[0] = __uint_as_float(0x4b000000u | s0);
+        f[1] = __uint_as_float(0x4b000000u | s1);
+        f[2] = __uint_as_float(0x4b000000u | s2);
+        f[3] = __uint_as_float(0x4b000000u | s3);
+    }
+}
+
 // threshold constant of one query in the magic-number domain: a code survives iff !(2^23 + LB > fma(v, -astep, b))
 __device__ __forceinline__ float ql_threshold_const(uint32_t thr_bits, float scale, float base, float mag) {
     const float thr = __uint_as_float(thr_bits);
@@ -710,20 +740,11 @@ scan_qlut_kernel(const ScanParams p, const QlParams ql) {
 
         // the filter on one code: packed lower bounds, then "2^23 + LB > threshold constant - astep * v" per query
         auto test = [&](const QlCode<M>& c) -> uint32_t {
-            uint2 lb = ql_block16(lutb, c.v[0], x8, x4, bsel, offs);
-#pragma unroll
-            for (int h = 1; h < M / 16; h++) {
-                const uint2 t_ = ql_block16(lutb + (h >> 1) * kQlPlaneBytes + (h & 1) * 128, c.v[h], x8, x4, bsel, offs);
-                lb.x += t_.x;
-                lb.y += t_.y;
-            }
+            float f[4];
+            ql_bounds_as_floats<M>(lutb, c.v, x8, x4, bsel, offs, f);
             const float vs = static_cast<float>(c.s);
-            const float f0 = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7410)),
-                        f1 = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7432)),
-                        f2 = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7410)),
-                        f3 = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7432));
-            const bool h0 = !(f0 > fmaf(vs, na[0], tb[0])), h1 = !(f1 > fmaf(vs, na[1], tb[1])),
-                       h2 = !(f2 > fmaf(vs, na[2], tb[2])), h3 = !(f3 > fmaf(vs, na[3], tb[3]));
+            const bool h0 = !(f[0] > fmaf(vs, na[0], tb[0])), h1 = !(f[1] > fmaf(vs, na[1], tb[1])),
+                       h2 = !(f[2] > fmaf(vs, na[2], tb[2])), h3 = !(f[3] > fmaf(vs, na[3], tb[3]));
             return (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u);
         };
         auto enqueue = [&](bool hit, uint32_t entry) {

@@ -666,20 +666,11 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
         }
 
         auto test = [&](const QlCode<M>& c) -> uint32_t {
-            uint2 lb = ql_block16(lutb, c.v[0], x8, x4, bsel, offs);
-#pragma unroll
-            for (int h = 1; h < M / 16; h++) {
-                const uint2 t_ = ql_block16(lutb + (h >> 1) * kQlPlaneBytes + (h & 1) * 128, c.v[h], x8, x4, bsel, offs);
-                lb.x += t_.x;
-                lb.y += t_.y;
-            }
+            float f[4];
+            ql_bounds_as_floats<M>(lutb, c.v, x8, x4, bsel, offs, f);
             const float vs = static_cast<float>(c.s);
-            const float f0 = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7410)),
-                        f1 = __uint_as_float(__byte_perm(lb.x, 0x4b000000u, 0x7432)),
-                        f2 = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7410)),
-                        f3 = __uint_as_float(__byte_perm(lb.y, 0x4b000000u, 0x7432));
-            const bool h0 = !(f0 > fmaf(vs, na[0], tb[0])), h1 = !(f1 > fmaf(vs, na[1], tb[1])),
-                       h2 = !(f2 > fmaf(vs, na[2], tb[2])), h3 = !(f3 > fmaf(vs, na[3], tb[3]));
+            const bool h0 = !(f[0] > fmaf(vs, na[0], tb[0])), h1 = !(f[1] > fmaf(vs, na[1], tb[1])),
+                       h2 = !(f[2] > fmaf(vs, na[2], tb[2])), h3 = !(f[3] > fmaf(vs, na[3], tb[3]));
             return (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u);
         };
         // survivors go straight to this warp's chunk of the global record buffer

@@ -62,10 +62,10 @@ def _check(oracle, a, xq, nprobe, k, what, repeats=2):
     (256, 12, 5000, 37, 3, 7, None, 16),        # dsub 16
     (80, 12, 5000, 40, 4, 10, None, 16),        # dsub 5
     (128, 4, 9000, 200, 4, 1, None, 16),        # k = 1, 200 queries on every list
-    (128, 24, 60000, 103, 5, 10, None, 32),     # M = 32 (C5 shape, dsub 4): two chunk tables, 10-bit entries
+    (128, 24, 60000, 103, 5, 10, None, 32),     # M = 32 (C5 shape, dsub 4): two chunk tables, sums widened per chunk
     (256, 16, 12000, 64, 16, 100, 13, 32),      # M = 32, dsub 8, k = 100, empty lists
     (192, 6, 2500, 9, 6, 10, None, 32),         # M = 32, dsub 6
-    (768, 12, 9000, 40, 4, 10, None, 64),       # M = 64 (C4 / RALM shape, dsub 12): four chunk tables, 9-bit entries
+    (768, 12, 9000, 40, 4, 10, None, 64),       # M = 64 (C4 / RALM shape, dsub 12): four chunk tables
     (128, 6, 2000, 9, 6, 20, 5, 64),            # M = 64, dsub 2, an empty list
     (128, 10, 30000, 64, 10, 500, None, 16),    # k = 500: shared-memory bitonic folds
 ])

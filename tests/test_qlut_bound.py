@@ -105,7 +105,7 @@ def make_case(seed, d, M, nlist, n, scale, shift, toy=False):
 
 @pytest.mark.parametrize("scale,shift,toy", [(1.0, 0.0, False), (255.0, 0.0, False), (1.0, 1000.0, False),
                                              (1e-3, 0.0, False), (3e4, 1e6, False), (1.0, 0.0, True)])
-@pytest.mark.parametrize("M,qmax", [(16, 2047), (32, 1023)])
+@pytest.mark.parametrize("M,qmax", [(16, 2047), (32, 2047)])
 def test_filter_never_drops_a_result(scale, shift, toy, M, qmax):
     d, nlist, n = 64, 6, 3000
     dsub = d // M
