@@ -124,6 +124,9 @@ struct b200_ivfpq_index {
     } pend;
     int st_mode = 1;            // B200_IVFPQ_STREAM=0: in-kernel top-k (scan_qlut_kernel) instead of the streaming pipeline
     double st_rate = 0.01;      // B200_IVFPQ_STREAM_RATE: survivor records provisioned per (query, code) pair
+    int st_two = 0;             // B200_IVFPQ_STREAM_TWO: 2 = use the two-query filter with bulk-async code tiles (M = 16).
+                                // Opt-in: measured SLOWER than the four-query kernel at every queries-per-list ratio
+                                // (profiles/r2_sweep_c2_two_query_filter.json), so `auto` never picks it
     int st_capq = 0;            // B200_IVFPQ_STREAM_CAPQ: keys per query slab (0 = max(1024, 32 k))
     double st_minrec = 4.0 * 1048576.0;   // B200_IVFPQ_STREAM_MINREC: lower bound of the record buffer (tests shrink it)
     float ql_pmax = 0.0f;
@@ -494,6 +497,16 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         int st_ctas = 0;
         StHostBuffers sb{};
         if (ql_ctas && h->st_mode) st_ctas = st_filter_grid(h->M, npairs, h->num_sms);
+        // opt-in experiment: work items of two pairs and the two-query filter kernel (scan_stream.cuh A2)
+        bool two = false;
+        if (st_ctas && h->M == 16 && !split && h->st_two == 2) {
+            const int g2 = st_filter2_grid(npairs, h->num_sms);
+            if (g2 > 0) {
+                two = true;
+                st_ctas = g2;
+            }
+        }
+        sb.gsz = two ? 2 : 4;
         if (st_ctas) {
             // survivor records: a share of the (query, code) pairs the batch scans; slabs: keys at or below a
             // query's bootstrap threshold.  An overflow is detected on the device and answered by the fallback launches.
@@ -532,7 +545,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             }
         }
         if (split && !ql_ctas) return fail(B200_IVFPQ_EUNSUPPORTED, "split search: the per-query-table scan does not apply here");
-        const int gsz = (quad_ctas || ql_ctas) ? 4 : 2;
+        const int gsz = two ? 2 : (quad_ctas || ql_ctas) ? 4 : 2;
         if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * quad_scratch_float4(h->M) * quad_ctas))) return rc;
 
         // pair setup
@@ -565,7 +578,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, (ql_ctas ? kQlGroupBytes : gsz == 4 ? sizeof(QuadGroup) : sizeof(DuoGroup)) * npairs, st));
             if (ql_ctas) {
                 if (ql_launch_scatter(probe32, npairs, nprobe, h->nlist, h->offsets.as<int64_t>(), h->start.as<int>(),
-                                      h->gstart.as<int>(), h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p, st))
+                                      h->gstart.as<int>(), h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p, gsz, st))
                     return fail(B200_IVFPQ_ECUDA, "pair scatter launch failed");
                 g_launches.fetch_add(1);
                 // one table per QUERY (not per pair): A_q quantised with the query's own scale
@@ -781,6 +794,8 @@ int b200_ivfpq_create(int d, int64_t nlist, int m, int nbits, b200_ivfpq_t* out)
     if (v) h->quad_drain_at = std::max(0, std::min(256, atoi(v)));
     v = getenv("B200_IVFPQ_STREAM");
     if (v) h->st_mode = atoi(v);
+    v = getenv("B200_IVFPQ_STREAM_TWO");
+    if (v) h->st_two = atoi(v);
     v = getenv("B200_IVFPQ_STREAM_CAPQ");
     if (v) h->st_capq = std::max(16, atoi(v));
     v = getenv("B200_IVFPQ_STREAM_MINREC");

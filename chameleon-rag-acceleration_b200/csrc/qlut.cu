@@ -106,10 +106,11 @@ int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nli
 }
 
 int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets,
-                      const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, cudaStream_t st) {
+                      const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, int gsz,
+                      cudaStream_t st) {
     ql_pair_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, nprobe, nlist, offsets, start,
                                                                            gstart, cursor, order,
-                                                                           static_cast<QlGroup*>(groups));
+                                                                           static_cast<QlGroup*>(groups), gsz);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -192,9 +193,16 @@ template <int M>
 int st_rest_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
               cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     if (ev0 && cudaEventRecord(ev0, st) != cudaSuccess) return -1;
-    const size_t fsm = st_filter_smem<M>();
-    if (cudaFuncSetAttribute(st_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
-    st_filter_kernel<M><<<(unsigned)filter_grid, QlCfg<M>::kT, fsm, st>>>(sp, ql, stp);
+    if (M == 16 && stp.gsz == 2) {
+        // lists probed by one or two queries: 32-bit table words, bulk-async code tiles
+        const size_t fsm = st_filter2_smem();
+        if (cudaFuncSetAttribute(st_filter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
+        st_filter2_kernel<<<(unsigned)filter_grid, 256, fsm, st>>>(sp, ql, stp);
+    } else {
+        const size_t fsm = st_filter_smem<M>();
+        if (cudaFuncSetAttribute(st_filter_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
+        st_filter_kernel<M><<<(unsigned)filter_grid, QlCfg<M>::kT, fsm, st>>>(sp, ql, stp);
+    }
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
     if (ev1 && cudaEventRecord(ev1, st) != cudaSuccess) return -1;
     st_eval_kernel<M><<<(unsigned)(8 * num_sms), 256, 0, st>>>(sp, stp);
@@ -228,6 +236,7 @@ void st_fill(const QlHostParams& qp, const StHostBuffers& sb, const int64_t* ids
     stp.qflag = static_cast<int*>(sb.qflag);
     stp.qkey = static_cast<uint64_t*>(sb.qkey);
     stp.capq = sb.capq;
+    stp.gsz = sb.gsz;
     stp.prefix = static_cast<uint32_t*>(sb.prefix);
     stp.pdis = static_cast<float*>(sb.pdis);
     stp.ids = ids;
@@ -240,6 +249,22 @@ void st_fill(const QlHostParams& qp, const StHostBuffers& sb, const int64_t* ids
 }
 
 }  // namespace
+
+int st_filter2_grid(int64_t npairs, int num_sms) {
+    const size_t smem = st_filter2_smem();
+    if (cudaFuncSetAttribute(st_filter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, st_filter2_kernel, 256, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    int64_t grid = static_cast<int64_t>(per_sm) * num_sms;
+    if (grid > npairs) grid = npairs;
+    return static_cast<int>(grid < 1 ? 1 : grid);
+}
 
 int st_filter_grid(int M, int64_t npairs, int num_sms) {
     switch (M) {

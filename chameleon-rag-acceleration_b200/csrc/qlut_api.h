@@ -45,7 +45,8 @@ constexpr int kQlHostBuckets = 3;
 int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets, int* hist,
                    PairStats* stats, cudaStream_t st);
 int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets,
-                      const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, cudaStream_t st);
+                      const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, int gsz,
+                      cudaStream_t st);
 int ql_launch_scan(const ScanParams& sp, const QlHostParams& qp, int grid, cudaStream_t st);
 
 // ---- streaming pipeline (scan_stream.cuh): bootstrap thresholds -> filter -> exact evaluation -> per-query select ----
@@ -59,12 +60,14 @@ struct StHostBuffers {
     void* qflag;              // nq * 4 bytes
     void* qkey;               // nq * 8 bytes
     int capq;
+    int gsz;                  // pairs per work item the groups were built with (4, or 2 for st_filter2_kernel)
     void* prefix;             // nq * nprobe * 4 bytes
     void* pdis;               // nq * nprobe * 4 bytes
 };
 constexpr size_t kStCtrBytes = 48;
 constexpr int kStChunkRecords = 64;
 int st_filter_grid(int M, int64_t npairs, int num_sms);        // 0: does not fit
+int st_filter2_grid(int64_t npairs, int num_sms);             // the two-query filter (M = 16)
 // enqueues the four kernels; the overflow flag (an int, != 0 after an overflow) lives at st_overflow_flag(ctr)
 // ev0 / ev1 (optional): recorded right before / after the filter kernel
 int st_launch(const ScanParams& sp, const QlHostParams& qp, const StHostBuffers& sb, int64_t nq, const int64_t* ids, float* D,

@@ -359,7 +359,7 @@ __global__ void ql_pair_hist_kernel(const int32_t* __restrict__ probe, int64_t n
 __global__ void ql_pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t npairs, int nprobe, int64_t nlist,
                                        const int64_t* __restrict__ offsets, const int* __restrict__ start,
                                        const int* __restrict__ gstart, int* __restrict__ cursor,
-                                       int32_t* __restrict__ order, QlGroup* __restrict__ groups) {
+                                       int32_t* __restrict__ order, QlGroup* __restrict__ groups, int gsz) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     int l = probe[i];
@@ -369,10 +369,12 @@ __global__ void ql_pair_scatter_kernel(const int32_t* __restrict__ probe, int64_
     const int64_t key = ql_bucket(static_cast<int>(i % nprobe)) * nlist + l;
     const int rank = atomicAdd(&cursor[key], 1);
     order[start[key] + rank] = static_cast<int32_t>(i);
-    QlGroup* g = groups + gstart[key] + (rank >> 2);
-    g->pair[rank & 3] = static_cast<int32_t>(i);
-    g->query[rank & 3] = static_cast<int32_t>(i / nprobe);
-    if ((rank & 3) == 0) {
+    // gsz = 4: four pairs per work item; gsz = 2: two (slots 2, 3 stay -1: the two-query filter, scan_stream.cuh)
+    const int slot = gsz == 4 ? (rank & 3) : (rank & 1);
+    QlGroup* g = groups + gstart[key] + (gsz == 4 ? (rank >> 2) : (rank >> 1));
+    g->pair[slot] = static_cast<int32_t>(i);
+    g->query[slot] = static_cast<int32_t>(i / nprobe);
+    if (slot == 0) {
         g->list = l;
         g->n = static_cast<uint32_t>(sz);
         g->beg = beg;

@@ -63,6 +63,7 @@ struct StParams {
     float* pdis;                      // (nq, nprobe) ||fl(q - c)||^2
     const int64_t* ids;
     int boot_codes;                   // candidates the bootstrap looks at (<= kStBootCodes)
+    int gsz;                          // pairs per work item: 4, or 2 (st_filter2_kernel)
     float* D;                         // (nq, k)
     int64_t* I;
 };
@@ -717,6 +718,290 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
             if (t0 + 3 < nblk) ST_ITER(c3, c1, 3)
         }
 #undef ST_ITER
+    }
+    if (lane == 0) {
+        if (chunk != 0xffffffffu) st.sfill[chunk] = fill;
+        if (nrec) atomicAdd(&st.ctr->records, static_cast<unsigned long long>(nrec));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A2: the filter for lists probed by ONE or TWO queries (few queries per list: small batches x nprobe, the RAG serving
+// regime, where every code byte comes from DRAM once).  M = 16.
+//   * Table entry = one 32-bit word (u_q0, u_q1): ONE LDS.32 wavefront serves two queries x 32 codes (the four-query
+//     layout spends an LDS.64 -- two wavefronts -- on the same look-up and wastes half of them on empty query slots).
+//     Row = code value, 256-byte stride, word (lane / 16) * 16 + (r ^ step): 32 distinct banks for any code bytes.
+//   * Code tiles arrive by BULK ASYNC COPY (cp.async.bulk global -> shared, completion on an mbarrier): a ring of kF2Stages
+//     tiles of 256 codes per CTA, issued by one thread, so kF2Stages x 4 KB per CTA are in flight without holding a
+//     register and without passing through the LSU on the way in.  Every warp releases a stage with one arrive on its
+//     `empty` mbarrier after it has copied its codes to registers (LDS.128, conflict-free).
+// Everything else (thresholds, survivor records, exact evaluation downstream) is st_filter_kernel's.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kF2Stages = 6;
+constexpr int kF2Tile = 256;                       // codes per stage (= threads)
+constexpr int kF2TileBytes = kF2Tile * 16;
+
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void st_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void st_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol error must end in a trap, not in a hung GPU
+__device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void st_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct StF2Ctrl {
+    int work;
+    int pad_[3];
+    float na[2];
+    float tb[2];
+    unsigned long long full[kF2Stages];
+    unsigned long long empty[kF2Stages];
+};
+
+__host__ __device__ inline size_t st_filter2_smem() {
+    return static_cast<size_t>(kQlPlaneBytes) + kF2Stages * kF2TileBytes + sizeof(StF2Ctrl) + 2 * sizeof(QlGroup);
+}
+
+// offsets of the 16 look-up steps for the 32-bit table: (lane / 16) * 64 + (r ^ p) * 4 (see ql_make_offsets)
+__device__ __forceinline__ QlOffsets st_make_offsets32(int lane) {
+    const int r = lane & 15, h = lane >> 4;
+    QlOffsets f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        uint32_t v = 0u;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const int p = 3 * i + b;
+            if (p < 16) v |= static_cast<uint32_t>(h * 64 + (r ^ p) * 4) << (8 * b);
+        }
+        f.o[i] = v;
+    }
+    return f;
+}
+template <int B, int P>
+__device__ __forceinline__ uint32_t st_lookup32(const char* __restrict__ lutb, uint32_t w, const QlOffsets& f) {
+    const uint32_t a = __byte_perm(w, f.o[P / 3], 0x7700u | (B << 4) | (4 + P % 3));
+    return *reinterpret_cast<const uint32_t*>(lutb + a);
+}
+__device__ __forceinline__ uint32_t st_block16_32(const char* __restrict__ lutb, const uint4& code, bool x8, bool x4,
+                                                  uint32_t bsel, const QlOffsets& f) {
+    const uint32_t y0 = x8 ? code.z : code.x, y1 = x8 ? code.w : code.y, y2 = x8 ? code.x : code.z,
+                   y3 = x8 ? code.y : code.w;
+    const uint32_t z0 = x4 ? y1 : y0, z1 = x4 ? y0 : y1, z2 = x4 ? y3 : y2, z3 = x4 ? y2 : y3;
+    const uint32_t w0 = __byte_perm(z0, 0u, bsel), w1 = __byte_perm(z1, 0u, bsel), w2 = __byte_perm(z2, 0u, bsel),
+                   w3 = __byte_perm(z3, 0u, bsel);
+    uint32_t s = 0u;
+#define ST_STEP(W, B, P) s += st_lookup32<B, P>(lutb, W, f);
+    ST_STEP(w0, 0, 0) ST_STEP(w0, 1, 1) ST_STEP(w0, 2, 2) ST_STEP(w0, 3, 3)
+    ST_STEP(w1, 0, 4) ST_STEP(w1, 1, 5) ST_STEP(w1, 2, 6) ST_STEP(w1, 3, 7)
+    ST_STEP(w2, 0, 8) ST_STEP(w2, 1, 9) ST_STEP(w2, 2, 10) ST_STEP(w2, 3, 11)
+    ST_STEP(w3, 0, 12) ST_STEP(w3, 1, 13) ST_STEP(w3, 2, 14) ST_STEP(w3, 3, 15)
+#undef ST_STEP
+    return s;
+}
+
+__global__ void __launch_bounds__(256, 2)
+st_filter2_kernel(const ScanParams p, const QlParams ql, const StParams st) {
+    constexpr int M = 16, kT = 256;
+    extern __shared__ __align__(1024) unsigned char smem_st[];
+    char* lutb = reinterpret_cast<char*>(smem_st);
+    unsigned char* ring = smem_st + kQlPlaneBytes;                               // kF2Stages tiles of 4 KB
+    StF2Ctrl* ctrl = reinterpret_cast<StF2Ctrl*>(ring + kF2Stages * kF2TileBytes);
+    QlGroup* s_grp = reinterpret_cast<QlGroup*>(ctrl + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r = lane & 15;
+    const QlOffsets offs = st_make_offsets32(lane);
+    const bool x8 = (r & 8) != 0, x4 = (r & 4) != 0;
+    const uint32_t bsel = (r & 3) == 0 ? 0x3210u : (r & 3) == 1 ? 0x2301u : (r & 3) == 2 ? 0x1032u : 0x0123u;
+    const int ngroups = p.stats->ngroups;
+    const int dsub = p.dsub;
+    unsigned int chunk = 0xffffffffu, fill = 0u, nrec = 0u;
+    bool dead = false;
+    uint32_t g = 0;          // tiles this CTA has consumed so far: stage = g % kF2Stages, phase = (g / kF2Stages) & 1
+    uint32_t gi = 0;         // tiles issued so far (thread 0)
+
+    if (tid == 0) {
+        for (int s = 0; s < kF2Stages; s++) {
+            st_mbar_init(st_smem_u32(&ctrl->full[s]), 1);
+            st_mbar_init(st_smem_u32(&ctrl->empty[s]), kT / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int next_work = 0, buf = 0;
+    if (tid == 0) {
+        next_work = atomicAdd(&p.stats->work_counter, 1);
+        if (next_work < ngroups) ql_copy_group_async(&s_grp[0], static_cast<const QlGroup*>(p.groups) + next_work);
+    }
+    for (;;) {
+        if (tid == 0) {
+            ctrl->work = next_work;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+        __syncthreads();   // every warp is done with the previous item's tables; all its tiles are consumed
+        const int wk = ctrl->work;
+        if (wk >= ngroups) break;
+        if (tid == 0) next_work = atomicAdd(&p.stats->work_counter, 1);
+        const QlGroup grp = s_grp[buf];
+        const bool has1 = grp.pair[1] >= 0;
+        const int q0 = grp.query[0], q1 = has1 ? grp.query[1] : grp.query[0];
+        const int list = grp.list;
+        const uint32_t n = grp.n;
+        const uint32_t nblk = (n + kT - 1) / kT;
+        const unsigned char* lcodes = p.codes + grp.beg * M;
+        const uint16_t* sp = ql.snorm + grp.beg;
+        // producer: the first tiles of this list go out before the table work starts
+        auto issue = [&](uint32_t blk) {   // thread 0 only
+            const uint32_t s = gi % kF2Stages;
+            if (gi >= kF2Stages) st_mbar_wait(st_smem_u32(&ctrl->empty[s]), ((gi / kF2Stages) - 1) & 1);
+            const uint32_t cnt = min(static_cast<uint32_t>(kT), n - blk * kT);
+            st_mbar_expect_tx(st_smem_u32(&ctrl->full[s]), cnt * 16u);
+            st_bulk_load(st_smem_u32(ring + s * kF2TileBytes), lcodes + static_cast<size_t>(blk) * kF2TileBytes, cnt * 16u,
+                         st_smem_u32(&ctrl->full[s]));
+            gi++;
+        };
+        uint32_t issued = 0;   // tiles of THIS list issued (thread 0)
+        if (tid == 0)
+            for (; issued < nblk && issued < kF2Stages - 1; issued++) issue(issued);
+        // pair constants: one thread per query
+        if (tid < 2) {
+            const int q = tid;
+            const bool has = q == 0 || has1;
+            const int pr = has ? grp.pair[0] * (1 - q) + (q ? grp.pair[1] : 0) : grp.pair[0];
+            const int qq = q == 0 ? q0 : q1;
+            const float c_sm = __ldg(ql.sbmin + list), c_st = __ldg(ql.sbstep + list);
+            const float a = __ldg(st.pdis + pr);
+            const float c_am = __ldg(ql.qamin + qq), c_s = __ldg(ql.qscale + qq);
+            const uint32_t thr = __ldg(p.qthr + qq);
+            const float dis0 = a * (1.0f - static_cast<float>(p.d + 5) * 5.9604645e-8f);
+            const float rn = sqrtf(a) * 1.00001f + ql.pmax;
+            const float E = static_cast<float>(dsub + M + 8) * 5.9604645e-8f * rn * rn * 1.00001f;
+            const float mag = fabsf(E) + fabsf(dis0) + fabsf(c_am) + fabsf(c_sm);
+            const float base = (((E - dis0) - c_am) - c_sm) + 4.8e-7f * mag;
+            ctrl->na[q] = -(c_s * c_st * 0.999999f);
+            ctrl->tb[q] = has ? ql_threshold_const(thr, c_s, base, mag) : -INFINITY;
+        }
+        // the two queries' tables: word (c, h, slot m) = (u_q0[c][m], u_q1[c][m]); a lane handles one row's slot pair
+        // (2 sp2, 2 sp2 + 1) and writes it to both half-warp copies
+        {
+            const int sp2 = lane & 7;
+#pragma unroll 1
+            for (int i0 = 0; i0 < 8; i0 += 4) {
+                uint32_t a0[4], a1[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int it = wid + (i0 + i) * (kT / 32);
+                    const int row = (it << 2) + (lane >> 3);
+                    a0[i] = __ldg(reinterpret_cast<const uint32_t*>(ql.qlut + (static_cast<int64_t>(q0) * 256 + row) * M) + sp2);
+                    a1[i] = __ldg(reinterpret_cast<const uint32_t*>(ql.qlut + (static_cast<int64_t>(q1) * 256 + row) * M) + sp2);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int it = wid + (i0 + i) * (kT / 32);
+                    const int row = (it << 2) + (lane >> 3);
+                    const uint2 e = make_uint2(__byte_perm(a0[i], a1[i], 0x5410), __byte_perm(a0[i], a1[i], 0x7632));
+                    *reinterpret_cast<uint2*>(lutb + row * 256 + sp2 * 8) = e;
+                    *reinterpret_cast<uint2*>(lutb + row * 256 + 64 + sp2 * 8) = e;
+                }
+            }
+        }
+        __syncthreads();
+        buf ^= 1;
+        if (tid == 0 && next_work < ngroups)
+            ql_copy_group_async(&s_grp[buf], static_cast<const QlGroup*>(p.groups) + next_work);
+        const float na0 = ctrl->na[0], na1 = ctrl->na[1], tb0 = ctrl->tb[0], tb1 = ctrl->tb[1];
+
+        uint32_t sn0 = tid < n ? __ldg(sp + tid) : 0u, sn1 = kT + tid < n ? __ldg(sp + kT + tid) : 0u;
+        // the code of block b + 1 is copied out of the ring (and its stage released) while block b is looked up
+        auto fetch = [&](uint32_t blk) -> uint4 {
+            const uint32_t s = g % kF2Stages;
+            st_mbar_wait(st_smem_u32(&ctrl->full[s]), (g / kF2Stages) & 1);
+            uint4 c = make_uint4(0u, 0u, 0u, 0u);
+            if (blk * kT + tid < n) c = *reinterpret_cast<const uint4*>(ring + s * kF2TileBytes + tid * 16);
+            g++;
+            return c;
+        };
+        uint4 code = fetch(0);
+        uint32_t rel = (g - 1) % kF2Stages;     // stage to release once `code` has been consumed
+#pragma unroll 1
+        for (uint32_t blk = 0; blk < nblk; blk++) {
+            const uint32_t idx = blk * kT + tid;
+            uint4 code_next = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t rel_next = 0u;
+            if (blk + 1 < nblk) {
+                code_next = fetch(blk + 1);
+                rel_next = (g - 1) % kF2Stages;
+            }
+            const uint32_t sn = sn0;
+            sn0 = sn1;
+            sn1 = idx + 2 * kT < n ? __ldg(sp + idx + 2 * kT) : 0u;
+            const uint32_t lb = st_block16_32(lutb, code, x8, x4, bsel, offs);
+            // the look-ups consumed the code registers, so this warp's reads of that stage are complete: release it,
+            // and (thread 0) refill the ring
+            __syncwarp();
+            if (lane == 0) st_mbar_arrive(st_smem_u32(&ctrl->empty[rel]));
+            if (tid == 0 && issued < nblk) {
+                issue(issued);
+                issued++;
+            }
+            code = code_next;
+            rel = rel_next;
+            const float vs = static_cast<float>(sn);
+            const float f0 = __uint_as_float(__byte_perm(lb, 0x4b000000u, 0x7410)),
+                        f1 = __uint_as_float(__byte_perm(lb, 0x4b000000u, 0x7432));
+            const bool h0 = !(f0 > fmaf(vs, na0, tb0)), h1 = !(f1 > fmaf(vs, na1, tb1));
+            const bool hit = idx < n && (h0 || h1);
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal != 0u && !dead) {
+                const unsigned np = __popc(bal);
+                if (chunk == 0xffffffffu || fill + np > kStChunk) {
+                    unsigned int c = 0u;
+                    if (lane == 0) {
+                        if (chunk != 0xffffffffu) st.sfill[chunk] = fill;
+                        c = atomicAdd(&st.ctr->nchunks, 1u);
+                    }
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    if (c >= st.max_chunks) {
+                        if (lane == 0) atomicOr(&st.ctr->overflow, 2);
+                        dead = true;
+                        chunk = 0xffffffffu;
+                    } else {
+                        chunk = c;
+                        fill = 0u;
+                    }
+                }
+                if (!dead) {
+                    if (hit) st.srec[static_cast<size_t>(chunk) * kStChunk + fill + __popc(bal & lanemask_lt())] =
+                                 make_uint2(static_cast<uint32_t>(wk), (idx << 4) | (h0 ? 1u : 0u) | (h1 ? 2u : 0u));
+                    fill += np;
+                    nrec += np;
+                }
+            }
+        }
     }
     if (lane == 0) {
         if (chunk != 0xffffffffu) st.sfill[chunk] = fill;

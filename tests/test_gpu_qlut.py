@@ -22,7 +22,7 @@ def _load(a, variant="qlut", stats=False, stream=1, env=None):
     with the in-kernel path as its overflow fallback); stream = 0: the in-kernel top-k path (scan_qlut_kernel) alone."""
     import b200ivfpq as faiss
     names = ("B200_IVFPQ_SCAN", "B200_IVFPQ_QL_STATS", "B200_IVFPQ_STREAM", "B200_IVFPQ_STREAM_MINREC",
-             "B200_IVFPQ_STREAM_RATE")
+             "B200_IVFPQ_STREAM_RATE", "B200_IVFPQ_STREAM_TWO")
     old = {k: os.environ.get(k) for k in names}
     os.environ["B200_IVFPQ_SCAN"] = variant
     os.environ["B200_IVFPQ_STREAM"] = str(stream)
@@ -166,6 +166,30 @@ def test_qlut_filter_actually_filters(oracle):
     codes = index.last_scan_stats()["codes"]
     assert out[2] > 0 and out[1] > 0
     assert out[1] < 0.1 * codes, f"{out[1]} exact evaluations for {codes} (query, code) pairs: the filter is not filtering"
+
+
+@pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used", [
+    (128, 24, 60000, 103, 5, 10, None),     # several tiles per list (ring of bulk-async tiles wraps), odd group sizes
+    (96, 16, 12000, 64, 16, 100, 13),       # dsub 6, k = 100, empty lists
+    (64, 8, 3000, 1, 8, 10, None),          # one query: every work item is a single
+    (128, 4, 9000, 200, 4, 1, None),        # k = 1, heavy ties
+    (128, 6, 300, 20, 6, 10, None),         # lists shorter than one tile
+])
+def test_two_query_filter_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
+    """st_filter2_kernel (work items of two pairs, 32-bit table words, cp.async.bulk code tiles on an mbarrier ring),
+    forced for every batch; `auto` picks it when lists are probed by at most two queries on average."""
+    a = _util.make_index_arrays(oracle, 290 + d, d, nlist, 16, n, used_lists=used)
+    if nlist == 4:
+        rng = np.random.default_rng(5)
+        a["codes"] = np.ascontiguousarray(a["codes"][rng.integers(0, 500, size=a["codes"].shape[0])])
+    xq = _util.make_queries(19, a, nq)
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+    index = _load(a, env={"B200_IVFPQ_STREAM_TWO": "2"})
+    index.nprobe = nprobe
+    for _ in range(3):
+        D, I = index.search(xq, k)
+        _util.assert_bit_equal(D, Dr, "D (two-query filter)")
+        _util.assert_bit_equal(I, Ir, "I (two-query filter)")
 
 
 def test_stream_overflow_falls_back(oracle):
