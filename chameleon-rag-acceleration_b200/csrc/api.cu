@@ -513,7 +513,11 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             const double visits = (double)npairs * (double)h->ntotal / (double)std::max<int64_t>(h->nonempty, 1);
             const double want = std::min(std::max(visits * h->st_rate, h->st_minrec), 192.0 * 1048576.0);
             sb.max_chunks = (unsigned int)(want / kStChunkRecords);
-            sb.capq = h->st_capq > 0 ? h->st_capq : std::max(4096, 32 * k);
+            // slabs: room for thousands of duplicate codes at a query's threshold distance (thresholds that came from
+            // another shard admit by distance only), within 2 GB per query chunk
+            sb.capq = h->st_capq > 0 ? h->st_capq
+                                     : (int)std::max<int64_t>(std::max(4096, 32 * k),
+                                                              std::min<int64_t>(16384, (int64_t(2) << 30) / (8 * std::max<int64_t>(qb, 1))));
             if ((rc = h->st_srec.ensure((size_t)sb.max_chunks * kStChunkRecords * 8))) return rc;
             if ((rc = h->st_sfill.ensure((size_t)sb.max_chunks * 4))) return rc;
             if ((rc = h->st_ctr.ensure(kStCtrBytes))) return rc;

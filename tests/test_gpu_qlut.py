@@ -192,6 +192,34 @@ def test_two_query_filter_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
         _util.assert_bit_equal(I, Ir, "I (two-query filter)")
 
 
+def test_split_search_begin_finish(oracle):
+    """b200_ivfpq_search_preassigned_begin / _finish (the multi-GPU threshold exchange) on one GPU: thresholds of all
+    queries, of half of them (the other half then has none: everything survives, the buffers overflow, the fallback
+    answers), and thresholds tightened by a second index holding the same vectors -- always the oracle's result."""
+    import torch
+    a, xq = _scaled(oracle, 31, 128, 16, 16, 50000, 96, 1.0, 0.0)
+    nprobe, k, nq = 6, 10, xq.shape[0]
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+    index = _load(a)
+    index.nprobe = nprobe
+    xq_t = torch.from_numpy(xq).cuda()
+    _, probes = index.quantizer.search(xq_t, nprobe)
+    for lo, hi in ((0, nq), (0, nq // 2), (nq // 3, nq)):
+        thr = index.search_preassigned_begin(xq_t, k, probes, lo, hi)
+        assert thr is not None, "the streaming pipeline applies to this shape"
+        t = thr.cpu().numpy()
+        assert (t[:lo] == 0x7f800000).all() and (t[hi:] == 0x7f800000).all() and (t[lo:hi] < 0x7f800000).all()
+        D, I = index.search_preassigned_finish(thr, nq, k)
+        _util.assert_bit_equal(D.cpu().numpy(), Dr, f"D (slice {lo}:{hi})")
+        _util.assert_bit_equal(I.cpu().numpy(), Ir, f"I (slice {lo}:{hi})")
+    # thresholds from elsewhere (here: the true k-th distances, the tightest valid ones) are applied by distance only
+    thr = index.search_preassigned_begin(xq_t, k, probes, 0, 0)
+    best = torch.from_numpy(np.ascontiguousarray(Dr[:, k - 1])).cuda().view(torch.int32)
+    D, I = index.search_preassigned_finish(torch.minimum(thr, best), nq, k)
+    _util.assert_bit_equal(D.cpu().numpy(), Dr, "D (exchanged thresholds)")
+    _util.assert_bit_equal(I.cpu().numpy(), Ir, "I (exchanged thresholds)")
+
+
 def test_stream_overflow_falls_back(oracle):
     """A survivor buffer far too small for the batch: the device raises the overflow flag and the guarded launches
     (in-kernel path + merge) answer; the results are the oracle's either way."""
