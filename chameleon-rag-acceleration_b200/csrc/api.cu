@@ -122,6 +122,19 @@ struct b200_ivfpq_index {
         int k = 0, nprobe = 0, st_ctas = 0, ql_ctas = 0;
         cudaStream_t st = nullptr;
     } pend;
+    cudaStream_t side = nullptr;              // per-query tables overlap the coarse stage on this stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_ok() {
+        if (side) return true;
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            side = nullptr;
+            return false;
+        }
+        return true;
+    }
     int st_mode = 1;            // B200_IVFPQ_STREAM=0: in-kernel top-k (scan_qlut_kernel) instead of the streaming pipeline
     double st_rate = 0.01;      // B200_IVFPQ_STREAM_RATE: survivor records provisioned per (query, code) pair
     int st_two = 0;             // B200_IVFPQ_STREAM_TWO: 2 = use the two-query filter with bulk-async code tiles (M = 16).
@@ -465,17 +478,6 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if (tm) h->ev = h->evs[h->timed_chunks].data();
         int32_t* probe32 = h->probe32.as<int32_t>();
 
-        if (tm) CUDA_TRY(cudaEventRecord(h->ev[0], st));
-        if (d_list_ids) {
-            probes_from_i64_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(d_list_ids + q0 * nprobe, probe32, npairs,
-                                                                       h->nlist);
-            LAUNCH_CHECK();
-            if (tm) CUDA_TRY(cudaEventRecord(h->ev[1], st));
-        } else {
-            if ((rc = run_coarse(h, nqc, xq, nprobe, probe32, nullptr, nullptr, st, tm))) return rc;
-        }
-        if (tm) CUDA_TRY(cudaEventRecord(h->ev[2], st));
-
         // which scan kernel will run decides how pairs are grouped (2 or 4 queries of a list per work item)
         const bool aligned16 = (reinterpret_cast<uintptr_t>(h->codes) & 15) == 0;
         int quad_ctas = 0;
@@ -552,6 +554,35 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         const int gsz = two ? 2 : (quad_ctas || ql_ctas) ? 4 : 2;
         if (quad_ctas && (rc = h->lutf.ensure(sizeof(float4) * quad_scratch_float4(h->M) * quad_ctas))) return rc;
 
+        // the per-query tables only need the queries: they are built on a side stream while the coarse quantizer and the
+        // pair set-up run (not under stream capture: the latency path's CUDA graph keeps one stream)
+        bool tables_async = false;
+        if (ql_ctas) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            CUDA_TRY(cudaStreamIsCapturing(st, &cs));
+            if (cs == cudaStreamCaptureStatusNone && h->side_ok()) {
+                CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+                CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                if (ql_build_query_tables(xq, nqc, h->pq, h->ql_mu.as<float>(), h->pq_maxnorm.as<float>(), h->d, h->M, h->dsub,
+                                          h->ql_lut.as<uint16_t>(), h->ql_scale.as<float>(), h->ql_amin.as<float>(), h->side))
+                    return fail(B200_IVFPQ_ECUDA, "query table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                g_launches.fetch_add(1);
+                CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
+                tables_async = true;
+            }
+        }
+
+        if (tm) CUDA_TRY(cudaEventRecord(h->ev[0], st));
+        if (d_list_ids) {
+            probes_from_i64_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(d_list_ids + q0 * nprobe, probe32, npairs,
+                                                                       h->nlist);
+            LAUNCH_CHECK();
+            if (tm) CUDA_TRY(cudaEventRecord(h->ev[1], st));
+        } else {
+            if ((rc = run_coarse(h, nqc, xq, nprobe, probe32, nullptr, nullptr, st, tm))) return rc;
+        }
+        if (tm) CUDA_TRY(cudaEventRecord(h->ev[2], st));
+
         // pair setup
         PairStats* stats = h->stats.as<PairStats>();
         const bool small_setup = nseg > 1 && npairs <= 8192 && npairs * nseg <= (1 << 17) && !quad_ctas && !ql_ctas;
@@ -562,13 +593,16 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
                                                         h->out_cnt.as<int>(), (int)(npairs * nseg), stats);
             LAUNCH_CHECK();
         } else {
-            const int64_t nkeys = ql_ctas ? h->nlist * kQlHostBuckets : h->nlist;
+            // (rank bucket, list) keys: the in-kernel path tightens thresholds as it goes and wants every query's nearest
+            // list first; the streaming filter's thresholds are fixed, it only needs "same list together"
+            const int nbuckets = (ql_ctas && !st_ctas) ? kQlHostBuckets : 1;
+            const int64_t nkeys = h->nlist * nbuckets;
             CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(int) * nkeys, st));
             CUDA_TRY(cudaMemsetAsync(h->out_cnt.p, 0, sizeof(int) * npairs * nseg, st));
             fill_u32_kernel<<<grid1d(nqc, 256), 256, 0, st>>>(h->qthr.as<uint32_t>(), nqc, kInfBits);
             LAUNCH_CHECK();
             if (ql_ctas) {
-                if (ql_launch_hist(probe32, npairs, nprobe, h->nlist, h->offsets.as<int64_t>(), h->hist.as<int>(), stats, st))
+                if (ql_launch_hist(probe32, npairs, nprobe, h->nlist, nbuckets, h->offsets.as<int64_t>(), h->hist.as<int>(), stats, st))
                     return fail(B200_IVFPQ_ECUDA, "pair histogram launch failed");
                 g_launches.fetch_add(1);
             } else {
@@ -581,16 +615,20 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             LAUNCH_CHECK();
             CUDA_TRY(cudaMemsetAsync(h->groups.p, 0xff, (ql_ctas ? kQlGroupBytes : gsz == 4 ? sizeof(QuadGroup) : sizeof(DuoGroup)) * npairs, st));
             if (ql_ctas) {
-                if (ql_launch_scatter(probe32, npairs, nprobe, h->nlist, h->offsets.as<int64_t>(), h->start.as<int>(),
+                if (ql_launch_scatter(probe32, npairs, nprobe, h->nlist, nbuckets, h->offsets.as<int64_t>(), h->start.as<int>(),
                                       h->gstart.as<int>(), h->hist.as<int>(), h->order.as<int32_t>(), h->groups.p, gsz, st))
                     return fail(B200_IVFPQ_ECUDA, "pair scatter launch failed");
                 g_launches.fetch_add(1);
                 // one table per QUERY (not per pair): A_q quantised with the query's own scale
-                if (ql_build_query_tables(xq, nqc, h->pq, h->ql_mu.as<float>(), h->pq_maxnorm.as<float>(), h->d, h->M,
-                                          h->dsub, h->ql_lut.as<uint16_t>(), h->ql_scale.as<float>(),
-                                          h->ql_amin.as<float>(), st))
-                    return fail(B200_IVFPQ_ECUDA, "query table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-                g_launches.fetch_add(1);
+                if (tables_async) {
+                    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
+                } else {
+                    if (ql_build_query_tables(xq, nqc, h->pq, h->ql_mu.as<float>(), h->pq_maxnorm.as<float>(), h->d, h->M,
+                                              h->dsub, h->ql_lut.as<uint16_t>(), h->ql_scale.as<float>(),
+                                              h->ql_amin.as<float>(), st))
+                        return fail(B200_IVFPQ_ECUDA, "query table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    g_launches.fetch_add(1);
+                }
             } else {
                 pair_scatter_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(probe32, npairs, h->offsets.as<int64_t>(),
                                                                         h->start.as<int>(), h->gstart.as<int>(),
@@ -830,6 +868,9 @@ int b200_ivfpq_destroy(b200_ivfpq_t h) {
     for (auto& kv : h->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (h->gstream) cudaStreamDestroy(h->gstream);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->pin_xq) cudaFreeHost(h->pin_xq);
     if (h->pin_D) cudaFreeHost(h->pin_D);
     if (h->pin_I) cudaFreeHost(h->pin_I);

@@ -99,17 +99,17 @@ int ql_build_query_tables(const float* xq, int64_t nq, const float* pq, const fl
     }
 }
 
-int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets, int* hist,
+int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, int nbuckets, const int64_t* offsets, int* hist,
                    PairStats* stats, cudaStream_t st) {
-    ql_pair_hist_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, nprobe, nlist, offsets, hist, stats);
+    ql_pair_hist_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, nprobe, nlist, nbuckets, offsets, hist, stats);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
-int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets,
+int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, int nbuckets, const int64_t* offsets,
                       const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, int gsz,
                       cudaStream_t st) {
-    ql_pair_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, nprobe, nlist, offsets, start,
-                                                                           gstart, cursor, order,
+    ql_pair_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, nprobe, nlist, nbuckets, offsets,
+                                                                           start, gstart, cursor, order,
                                                                            static_cast<QlGroup*>(groups), gsz);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }

@@ -42,9 +42,9 @@ int ql_build_query_tables(const float* xq, int64_t nq, const float* pq, const fl
                           int M, int dsub, uint16_t* qlut, float* qscale, float* qamin, cudaStream_t st);
 // pair setup with the key (rank bucket, list): hist / start / gstart / cursor hold kQlHostBuckets * nlist entries
 constexpr int kQlHostBuckets = 3;
-int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets, int* hist,
+int ql_launch_hist(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, int nbuckets, const int64_t* offsets, int* hist,
                    PairStats* stats, cudaStream_t st);
-int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, const int64_t* offsets,
+int ql_launch_scatter(const int32_t* probe, int64_t npairs, int nprobe, int64_t nlist, int nbuckets, const int64_t* offsets,
                       const int* start, const int* gstart, int* cursor, int32_t* order, void* groups, int gsz,
                       cudaStream_t st);
 int ql_launch_scan(const ScanParams& sp, const QlHostParams& qp, int grid, cudaStream_t st);

@@ -338,7 +338,7 @@ constexpr int kQlBuckets = 3;
 __device__ __forceinline__ int ql_bucket(int rank) { return rank == 0 ? 0 : rank < 4 ? 1 : 2; }
 
 __global__ void ql_pair_hist_kernel(const int32_t* __restrict__ probe, int64_t npairs, int nprobe, int64_t nlist,
-                                    const int64_t* __restrict__ offsets, int* __restrict__ hist,
+                                    int nbuckets, const int64_t* __restrict__ offsets, int* __restrict__ hist,
                                     PairStats* __restrict__ stats) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     unsigned long long codes = 0;
@@ -347,7 +347,7 @@ __global__ void ql_pair_hist_kernel(const int32_t* __restrict__ probe, int64_t n
         if (l >= 0) {
             int64_t sz = offsets[l + 1] - offsets[l];
             if (sz > 0) {
-                atomicAdd(&hist[ql_bucket(static_cast<int>(i % nprobe)) * nlist + l], 1);
+                atomicAdd(&hist[(nbuckets == 1 ? 0 : ql_bucket(static_cast<int>(i % nprobe))) * nlist + l], 1);
                 codes = static_cast<unsigned long long>(sz);
             }
         }
@@ -357,7 +357,7 @@ __global__ void ql_pair_hist_kernel(const int32_t* __restrict__ probe, int64_t n
 }
 
 __global__ void ql_pair_scatter_kernel(const int32_t* __restrict__ probe, int64_t npairs, int nprobe, int64_t nlist,
-                                       const int64_t* __restrict__ offsets, const int* __restrict__ start,
+                                       int nbuckets, const int64_t* __restrict__ offsets, const int* __restrict__ start,
                                        const int* __restrict__ gstart, int* __restrict__ cursor,
                                        int32_t* __restrict__ order, QlGroup* __restrict__ groups, int gsz) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -366,7 +366,7 @@ __global__ void ql_pair_scatter_kernel(const int32_t* __restrict__ probe, int64_
     if (l < 0) return;
     const int64_t beg = offsets[l], sz = offsets[l + 1] - beg;
     if (sz <= 0) return;
-    const int64_t key = ql_bucket(static_cast<int>(i % nprobe)) * nlist + l;
+    const int64_t key = (nbuckets == 1 ? 0 : ql_bucket(static_cast<int>(i % nprobe))) * nlist + l;
     const int rank = atomicAdd(&cursor[key], 1);
     order[start[key] + rank] = static_cast<int32_t>(i);
     // gsz = 4: four pairs per work item; gsz = 2: two (slots 2, 3 stay -1: the two-query filter, scan_stream.cuh)
