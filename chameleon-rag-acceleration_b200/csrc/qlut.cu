@@ -205,7 +205,17 @@ int st_rest_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int
     }
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
     if (ev1 && cudaEventRecord(ev1, st) != cudaSuccess) return -1;
-    st_eval_kernel<M><<<(unsigned)(8 * num_sms), 256, 0, st>>>(sp, stp);
+    {
+        const size_t esm = st_eval_smem(M, sp.dsub);
+        if (esm <= kStEvalSmemMax) {
+            // the PQ codebook fits shared memory: one CTA per SM, codebook rows gathered with LDS
+            if (cudaFuncSetAttribute(st_eval_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm) != cudaSuccess)
+                return -1;
+            st_eval_kernel<M, true><<<(unsigned)num_sms, kStEvalThreads, esm, st>>>(sp, stp);
+        } else {
+            st_eval_kernel<M, false><<<(unsigned)(2 * num_sms), kStEvalThreads, 0, st>>>(sp, stp);
+        }
+    }
     if (cudaPeekAtLastError() != cudaSuccess) return -1;
     const size_t ssm = TopK::smem_bytes(sp.k, kStSelCap);
     if (ssm > 48 * 1024 &&

@@ -1010,15 +1010,78 @@ st_filter2_kernel(const ScanParams p, const QlParams ql, const StParams st) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// B: exact evaluation of the survivors
+// B: exact evaluation of the survivors.  One thread per record.  The 16 (M) codebook rows a record needs are random
+// gathers: from global memory every lane of an LDG touches its own cache line (32 L1 wavefronts per instruction; ncu on
+// C2: that is the kernel's whole run time), so the PQ codebook is staged in shared memory when it fits (128 KB at
+// d = 128, rows padded so that random rows spread over the banks) and the gathers become LDS.
 // ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int st_eval_row_stride(int dsub) { return dsub + ((dsub & 3) == 0 ? 4 : (dsub & 1) == 0 ? 2 : 1); }
+__host__ __device__ inline size_t st_eval_smem(int M, int dsub) {
+    return sizeof(float) * static_cast<size_t>(M) * 256 * st_eval_row_stride(dsub);
+}
+constexpr int kStEvalThreads = 1024;
+constexpr size_t kStEvalSmemMax = 200 * 1024;
+
+// pq_rows: codebook rows with `stride` floats between them (global: stride = dsub; shared: padded)
 template <int M>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float st_exact_rows(const uint8_t* __restrict__ code, const float* __restrict__ q,
+                                               const float* __restrict__ c, const float* __restrict__ pq_rows, int dsub,
+                                               int stride) {
+    float acc = 0.0f;
+#pragma unroll 1
+    for (int m0 = 0; m0 < M; m0 += 4) {
+        const uint32_t cw = __ldg(reinterpret_cast<const uint32_t*>(code + m0));
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int m = m0 + b;
+            const uint32_t cv = (cw >> (8 * b)) & 255u;
+            const float* pc = pq_rows + (static_cast<int64_t>(m) * 256 + cv) * stride;
+            const float* qq = q + m * dsub;
+            const float* cc = c + m * dsub;
+            float t = 0.0f;
+            if ((dsub & 3) == 0) {
+                for (int j = 0; j < dsub; j += 4) {
+                    const float4 pv = *reinterpret_cast<const float4*>(pc + j);
+                    const float4 qv = __ldg(reinterpret_cast<const float4*>(qq + j));
+                    const float4 cv4 = __ldg(reinterpret_cast<const float4*>(cc + j));
+                    t = sqdiff_acc(t, __fsub_rn(qv.x, cv4.x), pv.x);
+                    t = sqdiff_acc(t, __fsub_rn(qv.y, cv4.y), pv.y);
+                    t = sqdiff_acc(t, __fsub_rn(qv.z, cv4.z), pv.z);
+                    t = sqdiff_acc(t, __fsub_rn(qv.w, cv4.w), pv.w);
+                }
+            } else if ((dsub & 1) == 0) {
+                for (int j = 0; j < dsub; j += 2) {
+                    const float2 pv = *reinterpret_cast<const float2*>(pc + j);
+                    const float2 qv = __ldg(reinterpret_cast<const float2*>(qq + j));
+                    const float2 cv2 = __ldg(reinterpret_cast<const float2*>(cc + j));
+                    t = sqdiff_acc(t, __fsub_rn(qv.x, cv2.x), pv.x);
+                    t = sqdiff_acc(t, __fsub_rn(qv.y, cv2.y), pv.y);
+                }
+            } else {
+                for (int j = 0; j < dsub; j++) t = sqdiff_acc(t, __fsub_rn(__ldg(qq + j), __ldg(cc + j)), pc[j]);
+            }
+            acc = __fadd_rn(acc, t);
+        }
+    }
+    return acc;
+}
+
+template <int M, bool SMEM_PQ>
+__global__ void __launch_bounds__(kStEvalThreads)
 st_eval_kernel(const ScanParams p, const StParams st) {
-    const unsigned int nchunks = min(st.ctr->nchunks, st.max_chunks);
+    extern __shared__ __align__(16) float st_spq[];
     const int tid = threadIdx.x;
+    const int stride = SMEM_PQ ? st_eval_row_stride(p.dsub) : p.dsub;
+    const float* pq_rows = p.pq;
+    if (SMEM_PQ) {
+        for (int e = tid; e < M * 256 * p.dsub; e += kStEvalThreads) st_spq[(e / p.dsub) * stride + e % p.dsub] = __ldg(p.pq + e);
+        pq_rows = st_spq;
+        __syncthreads();
+    }
+    const unsigned int nchunks = min(st.ctr->nchunks, st.max_chunks);
+    constexpr unsigned int kPer = kStEvalThreads / kStChunk;   // chunks per CTA and iteration
     unsigned long long nev = 0ull;
-    for (unsigned int c0 = blockIdx.x * 4u; c0 < nchunks; c0 += gridDim.x * 4u) {
+    for (unsigned int c0 = blockIdx.x * kPer; c0 < nchunks; c0 += gridDim.x * kPer) {
         const unsigned int c = c0 + (tid >> 6);
         const unsigned int slot = tid & 63;
         if (c >= nchunks || slot >= st.sfill[c]) continue;
@@ -1034,7 +1097,8 @@ st_eval_kernel(const ScanParams p, const StParams st) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1u;
             const int pair = g->pair[b], q = g->query[b];
-            const uint32_t db = __float_as_uint(st_exact<M>(code, p.xq + static_cast<int64_t>(q) * p.d, crow, p.pq, p.dsub));
+            const uint32_t db = __float_as_uint(
+                st_exact_rows<M>(code, p.xq + static_cast<int64_t>(q) * p.d, crow, pq_rows, p.dsub, stride));
             nev++;
             const uint64_t key = make_key(db, __ldg(st.prefix + pair) + idx);
             if (key <= __ldg(st.qkey + q)) {
