@@ -140,7 +140,7 @@ st_boot_kernel(const float* __restrict__ xq, const float* __restrict__ cent, con
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t q = blockIdx.x;
     for (int j = tid; j < d; j += kStBootThreads) qv[j] = xq[q * d + j];
-    {
+    if (q >= boot_lo && q < boot_hi) {   // (the other queries only need their scan positions and coarse distances)
         const uint32_t* src = reinterpret_cast<const uint32_t*>(ql.qlut + q * 256 * M);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_lut);
         for (int i = tid; i < 256 * M / 2; i += kStBootThreads) dst[(i / (M / 2)) * (kRow / 2) + (i % (M / 2))] = __ldg(src + i);
@@ -328,7 +328,7 @@ st_boot_warp_kernel(const float* __restrict__ xq, const float* __restrict__ cent
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t q = blockIdx.x;
     for (int j = tid; j < d; j += kStBootThreads) qv[j] = xq[q * d + j];
-    {
+    if (q >= boot_lo && q < boot_hi) {   // (the other queries only need their scan positions and coarse distances)
         const uint32_t* src = reinterpret_cast<const uint32_t*>(ql.qlut + q * 256 * M);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_lut);
         for (int i = tid; i < 256 * M / 2; i += kStBootThreads) dst[(i / (M / 2)) * (kRow / 2) + (i % (M / 2))] = __ldg(src + i);
@@ -626,32 +626,50 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
             ctrl->na[q] = -(c_s * c_st * 0.999999f);
             ctrl->tb[q] = has ? ql_threshold_const(thr, c_s, base, mag) : -INFINITY;
         }
-        // the four queries' tables, interleaved entry-wise (see scan_qlut_kernel)
+        // the four queries' tables, interleaved entry-wise (see scan_qlut_kernel).  Every lane moves 16-byte pieces: one
+        // LDG.128 per query fetches 8 entries (a warp reads 512 contiguous bytes of a table: 4 L1 wavefronts instead of the
+        // 16 that four 32-bit loads of the same bytes take -- at 8 shards the copy was a third of the kernel's L1 traffic),
+        // four STS.128 write them back interleaved.  The lanes of a quarter-warp would all write the same two 16-byte
+        // columns; rotating the word order by (piece index / 2) % 4 spreads them over all eight: conflict-free.
         {
-            const int sp2 = lane & 7;
-            constexpr int kSteps = Cfg::kChunks * 64 / (kT / 32);
+            constexpr int kPieces = M / 8;            // 16-byte pieces per table row = pieces per thread
+            constexpr int kBatch = 2;
 #pragma unroll 1
-            for (int i0 = 0; i0 < kSteps; i0 += 8) {
-                uint32_t a[8][Q];
+            for (int i0 = 0; i0 < kPieces; i0 += kBatch) {
+                uint4 a[kBatch][Q];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int it = wid + (i0 + i) * (kT / 32);
-                    const int h = it >> 6, row = ((it & 63) << 2) + (lane >> 3);
+                for (int i = 0; i < kBatch; i++) {
+                    const int t = (i0 + i) * kT + tid;
 #pragma unroll
                     for (int q = 0; q < Q; q++)
-                        a[i][q] = __ldg(reinterpret_cast<const uint32_t*>(ql.qlut + (static_cast<int64_t>(qi[q]) * 256 + row) * M) +
-                                        h * 8 + sp2);
+                        a[i][q] = __ldg(reinterpret_cast<const uint4*>(ql.qlut + static_cast<int64_t>(qi[q]) * 256 * M) + t);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int it = wid + (i0 + i) * (kT / 32);
-                    const int h = it >> 6, row = ((it & 63) << 2) + (lane >> 3);
-                    uint4 e;
-                    e.x = __byte_perm(a[i][0], a[i][1], 0x5410);
-                    e.y = __byte_perm(a[i][2], a[i][3], 0x5410);
-                    e.z = __byte_perm(a[i][0], a[i][1], 0x7632);
-                    e.w = __byte_perm(a[i][2], a[i][3], 0x7632);
-                    *reinterpret_cast<uint4*>(lutb + (h >> 1) * kQlPlaneBytes + row * 256 + (h & 1) * 128 + sp2 * 16) = e;
+                for (int i = 0; i < kBatch; i++) {
+                    const int t = (i0 + i) * kT + tid;
+                    const int row = t / kPieces, piece = t % kPieces, h = piece >> 1, half = piece & 1;
+                    const int rot = (t >> 1) & 3;
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        uint4 v = a[i][q];
+                        if (rot & 1) v = make_uint4(v.y, v.z, v.w, v.x);
+                        if (rot & 2) v = make_uint4(v.z, v.w, v.x, v.y);
+                        a[i][q] = v;
+                    }
+                    char* dst = lutb + (h >> 1) * kQlPlaneBytes + row * 256 + (h & 1) * 128 + half * 64;
+                    const uint32_t w[4][Q] = {{a[i][0].x, a[i][1].x, a[i][2].x, a[i][3].x},
+                                              {a[i][0].y, a[i][1].y, a[i][2].y, a[i][3].y},
+                                              {a[i][0].z, a[i][1].z, a[i][2].z, a[i][3].z},
+                                              {a[i][0].w, a[i][1].w, a[i][2].w, a[i][3].w}};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint4 e;
+                        e.x = __byte_perm(w[j][0], w[j][1], 0x5410);
+                        e.y = __byte_perm(w[j][2], w[j][3], 0x5410);
+                        e.z = __byte_perm(w[j][0], w[j][1], 0x7632);
+                        e.w = __byte_perm(w[j][2], w[j][3], 0x7632);
+                        *reinterpret_cast<uint4*>(dst + ((j + rot) & 3) * 16) = e;
+                    }
                 }
             }
         }
