@@ -137,9 +137,9 @@ struct b200_ivfpq_index {
     }
     int st_mode = 1;            // B200_IVFPQ_STREAM=0: in-kernel top-k (scan_qlut_kernel) instead of the streaming pipeline
     double st_rate = 0.01;      // B200_IVFPQ_STREAM_RATE: survivor records provisioned per (query, code) pair
-    int st_two = 0;             // B200_IVFPQ_STREAM_TWO: 2 = use the two-query filter with bulk-async code tiles (M = 16).
-                                // Opt-in: measured SLOWER than the four-query kernel at every queries-per-list ratio
-                                // (profiles/r2_sweep_c2_two_query_filter.json), so `auto` never picks it
+    int st_two = -1;            // B200_IVFPQ_STREAM_TWO: -1 auto (two-query LDS.32 filter when npairs <= nlist, M = 16),
+                                // 0 never, 1 always, 2 = the two-query filter with bulk-async code tiles: measured SLOWER
+                                // than the four-query kernel everywhere (profiles/r2_sweep_c2_two_query_filter.json)
     int st_capq = 0;            // B200_IVFPQ_STREAM_CAPQ: keys per query slab (0 = max(1024, 32 k))
     double st_minrec = 4.0 * 1048576.0;   // B200_IVFPQ_STREAM_MINREC: lower bound of the record buffer (tests shrink it)
     float ql_pmax = 0.0f;
@@ -499,13 +499,22 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         int st_ctas = 0;
         StHostBuffers sb{};
         if (ql_ctas && h->st_mode) st_ctas = st_filter_grid(h->M, npairs, h->num_sms);
-        // opt-in experiment: work items of two pairs and the two-query filter kernel (scan_stream.cuh A2)
+        // Lists probed by one or two queries (at most one pair per list on average): work items of two pairs and 32-bit
+        // table words -- half the shared-memory wavefronts per code (st_filter_kernel<16, true>).
+        // B200_IVFPQ_STREAM_TWO: 0 never, 1 always, 2 = the bulk-async experiment (scan_stream.cuh A2), default auto
         bool two = false;
-        if (st_ctas && h->M == 16 && !split && h->st_two == 2) {
-            const int g2 = st_filter2_grid(npairs, h->num_sms);
-            if (g2 > 0) {
+        sb.two_kind = 0;
+        if (st_ctas && h->M == 16) {
+            if (h->st_two == 2 && !split) {
+                const int g2 = st_filter2_grid(npairs, h->num_sms);
+                if (g2 > 0) {
+                    two = true;
+                    sb.two_kind = 2;
+                    st_ctas = g2;
+                }
+            } else if (h->st_two == 1 || (h->st_two < 0 && npairs <= h->nlist)) {
                 two = true;
-                st_ctas = g2;
+                sb.two_kind = 1;
             }
         }
         sb.gsz = two ? 2 : 4;

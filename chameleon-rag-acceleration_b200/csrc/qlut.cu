@@ -193,8 +193,15 @@ template <int M>
 int st_rest_t(const ScanParams& sp, const QlParams& ql, const StParams& stp, int64_t nq, int filter_grid, int num_sms,
               cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     if (ev0 && cudaEventRecord(ev0, st) != cudaSuccess) return -1;
-    if (M == 16 && stp.gsz == 2) {
-        // lists probed by one or two queries: 32-bit table words, bulk-async code tiles
+    if (M == 16 && stp.gsz == 2 && stp.two_kind != 2) {
+        // lists probed by one or two queries: 32-bit table words, the four-query kernel's register pipeline
+        constexpr int M16 = 16;
+        const size_t fsm = st_filter_smem<M16>();
+        if (cudaFuncSetAttribute(st_filter_kernel<M16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess)
+            return -1;
+        st_filter_kernel<M16, true><<<(unsigned)filter_grid, QlCfg<M16>::kT, fsm, st>>>(sp, ql, stp);
+    } else if (M == 16 && stp.gsz == 2) {
+        // opt-in experiment: 32-bit table words, bulk-async code tiles
         const size_t fsm = st_filter2_smem();
         if (cudaFuncSetAttribute(st_filter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm) != cudaSuccess) return -1;
         st_filter2_kernel<<<(unsigned)filter_grid, 256, fsm, st>>>(sp, ql, stp);
@@ -247,6 +254,7 @@ void st_fill(const QlHostParams& qp, const StHostBuffers& sb, const int64_t* ids
     stp.qkey = static_cast<uint64_t*>(sb.qkey);
     stp.capq = sb.capq;
     stp.gsz = sb.gsz;
+    stp.two_kind = sb.two_kind;
     stp.prefix = static_cast<uint32_t*>(sb.prefix);
     stp.pdis = static_cast<float*>(sb.pdis);
     stp.ids = ids;

@@ -60,7 +60,8 @@ struct StHostBuffers {
     void* qflag;              // nq * 4 bytes
     void* qkey;               // nq * 8 bytes
     int capq;
-    int gsz;                  // pairs per work item the groups were built with (4, or 2 for st_filter2_kernel)
+    int gsz;                  // pairs per work item the groups were built with (4, or 2 for the two-query filters)
+    int two_kind;             // gsz == 2: 1 = st_filter_kernel<16, true> (LDS.32 tables), 2 = st_filter2_kernel (bulk-async)
     void* prefix;             // nq * nprobe * 4 bytes
     void* pdis;               // nq * nprobe * 4 bytes
 };

@@ -457,6 +457,49 @@ __device__ __forceinline__ uint2 ql_block16(const char* __restrict__ lutb, const
     return make_uint2(s01, s23);
 }
 
+// Two queries per work item (lists probed by one or two queries: small batches x nprobe): a table entry is ONE 32-bit
+// word (u_q0 | u_q1 << 16), so a look-up is an LDS.32 -- one shared-memory wavefront per warp instead of the two an LDS.64
+// takes, which the four-query layout wastes on empty query slots there.  Row = code value (256-byte stride as above),
+// word (lane / 16) * 16 + (r ^ step): the table is stored twice per row so that the two half-warps -- which walk
+// different codes -- use disjoint banks: 32 distinct banks for ANY code bytes.
+__device__ __forceinline__ QlOffsets ql_make_offsets_two(int lane) {
+    const int r = lane & 15, half = lane >> 4;
+    QlOffsets f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        uint32_t v = 0u;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const int p = 3 * i + b;
+            if (p < 16) v |= static_cast<uint32_t>(half * 64 + (r ^ p) * 4) << (8 * b);
+        }
+        f.o[i] = v;
+    }
+    return f;
+}
+template <int B, int P>
+__device__ __forceinline__ uint32_t ql_lookup_two(const char* __restrict__ lutb, uint32_t w, const QlOffsets& f) {
+    const uint32_t a = __byte_perm(w, f.o[P / 3], 0x7700u | (B << 4) | (4 + P % 3));
+    return *reinterpret_cast<const uint32_t*>(lutb + a);
+}
+// packed lower bounds (q0 | q1 << 16) of one 16-byte code; each half <= 16 * 2047 < 2^16: no carry between the halves
+__device__ __forceinline__ uint32_t ql_block16_two(const char* __restrict__ lutb, const uint4& code, bool x8, bool x4,
+                                                   uint32_t bsel, const QlOffsets& f) {
+    const uint32_t y0 = x8 ? code.z : code.x, y1 = x8 ? code.w : code.y, y2 = x8 ? code.x : code.z,
+                   y3 = x8 ? code.y : code.w;
+    const uint32_t z0 = x4 ? y1 : y0, z1 = x4 ? y0 : y1, z2 = x4 ? y3 : y2, z3 = x4 ? y2 : y3;
+    const uint32_t w0 = __byte_perm(z0, 0u, bsel), w1 = __byte_perm(z1, 0u, bsel), w2 = __byte_perm(z2, 0u, bsel),
+                   w3 = __byte_perm(z3, 0u, bsel);
+    uint32_t sa = 0u, sb = 0u;   // two chains
+#define QL_STEP2(S, W, B, P) S += ql_lookup_two<B, P>(lutb, W, f);
+    QL_STEP2(sa, w0, 0, 0) QL_STEP2(sb, w0, 1, 1) QL_STEP2(sa, w0, 2, 2) QL_STEP2(sb, w0, 3, 3)
+    QL_STEP2(sa, w1, 0, 4) QL_STEP2(sb, w1, 1, 5) QL_STEP2(sa, w1, 2, 6) QL_STEP2(sb, w1, 3, 7)
+    QL_STEP2(sa, w2, 0, 8) QL_STEP2(sb, w2, 1, 9) QL_STEP2(sa, w2, 2, 10) QL_STEP2(sb, w2, 3, 11)
+    QL_STEP2(sa, w3, 0, 12) QL_STEP2(sb, w3, 1, 13) QL_STEP2(sa, w3, 2, 14) QL_STEP2(sb, w3, 3, 15)
+#undef QL_STEP2
+    return sa + sb;
+}
+
 __device__ __forceinline__ void ql_copy_group_async(QlGroup* dst, const QlGroup* src) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
     const char* s = reinterpret_cast<const char*>(src);

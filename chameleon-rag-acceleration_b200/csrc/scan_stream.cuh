@@ -63,7 +63,8 @@ struct StParams {
     float* pdis;                      // (nq, nprobe) ||fl(q - c)||^2
     const int64_t* ids;
     int boot_codes;                   // candidates the bootstrap looks at (<= kStBootCodes)
-    int gsz;                          // pairs per work item: 4, or 2 (st_filter2_kernel)
+    int gsz;                          // pairs per work item: 4, or 2 (the two-query filters)
+    int two_kind;                     // gsz == 2: 1 = st_filter_kernel<16, true>, 2 = st_filter2_kernel (bulk-async tiles)
     float* D;                         // (nq, k)
     int64_t* I;
 };
@@ -556,9 +557,11 @@ __host__ __device__ inline size_t st_filter_smem() {
     return static_cast<size_t>(QlCfg<M>::kLutBytes) + sizeof(StCtrl) + 2 * sizeof(QlGroup);
 }
 
-template <int M>
+// TWO: work items of at most two pairs and the 32-bit table words of ql_block16_two (M = 16)
+template <int M, bool TWO = false>
 __global__ void __launch_bounds__(QlCfg<M>::kT, M == 64 ? 1 : 3)
 st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
+    static_assert(!TWO || M == 16, "the two-query table layout is one 16-byte chunk per code");
     using Cfg = QlCfg<M>;
     constexpr int kT = Cfg::kT;
     constexpr int Q = kQlQ;
@@ -567,9 +570,9 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
     StCtrl* ctrl = reinterpret_cast<StCtrl*>(smem_st + Cfg::kLutBytes);
     QlGroup* s_grp = reinterpret_cast<QlGroup*>(ctrl + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int r = lane & 15;
-    const QlOffsets offs = ql_make_offsets(r);
+    const QlOffsets offs = TWO ? ql_make_offsets_two(lane) : ql_make_offsets(r);
     const bool x8 = (r & 8) != 0, x4 = (r & 4) != 0;
     const uint32_t bsel = (r & 3) == 0 ? 0x3210u : (r & 3) == 1 ? 0x2301u : (r & 3) == 2 ? 0x1032u : 0x0123u;
     const int ngroups = p.stats->ngroups;
@@ -606,7 +609,34 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
         const uint4* lp = reinterpret_cast<const uint4*>(p.codes + grp.beg * M);
         const uint16_t* sp = ql.snorm + grp.beg;
         // first codes in flight before the set-up work
-        QlCode<M> c0 = ql_load_code<M>(lp, sp, tid, n), c1 = ql_load_code<M>(lp, sp, kT + tid, n), c2, c3;
+        QlCode<M> c0, c1, c2, c3;
+        // TWO: the codes arrive by cp.async (L1 bypass) in a ring of kRing blocks of 256 codes that lives in the half of
+        // the 256-byte table rows the two-query tables leave free.  Every thread copies, waits for and reads back ITS OWN
+        // 16 bytes: no barrier, no register per byte in flight -- kRing - 1 blocks (28 KB per CTA) are outstanding, which
+        // is what a DRAM-bound scan needs (one query per list: every code byte comes from HBM once)
+        constexpr uint32_t kRing = 8;
+        const uint32_t ring0 = static_cast<uint32_t>(__cvta_generic_to_shared(lutb + (tid >> 3) * 256 + 128 + (tid & 7) * 16));
+        auto ring_issue = [&](uint32_t blk) {
+            const uint32_t idx = blk * kT + tid;
+            if (idx < n)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + (blk & (kRing - 1)) * 8192u), "l"(lp + idx)
+                             : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto load_sn = [&](uint32_t blk) -> uint32_t {
+            const uint32_t idx = blk * kT + tid;
+            return idx < n ? static_cast<uint32_t>(__ldg(sp + idx)) : 0u;
+        };
+        uint32_t snA = 0u, snB = 0u;
+        if constexpr (TWO) {
+#pragma unroll
+            for (uint32_t b = 0; b + 1 < kRing; b++) ring_issue(b);
+            snA = load_sn(0);
+            snB = load_sn(1);
+        } else {
+            c0 = ql_load_code<M>(lp, sp, tid, n);
+            c1 = ql_load_code<M>(lp, sp, kT + tid, n);
+        }
         // pair constants: one thread per query, through shared memory (read after the barrier below)
         if (tid < Q) {
             const int q = tid;
@@ -631,6 +661,32 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
         // 16 that four 32-bit loads of the same bytes take -- at 8 shards the copy was a third of the kernel's L1 traffic),
         // four STS.128 write them back interleaved.  The lanes of a quarter-warp would all write the same two 16-byte
         // columns; rotating the word order by (piece index / 2) % 4 spreads them over all eight: conflict-free.
+        if constexpr (TWO) {
+            // two tables -> (u_q0 | u_q1 << 16) words, written to both halves of the row's 128 bytes.  A lane's four
+            // 16-byte stores go out in an order rotated by its row: the quarter-warp covers all eight columns
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int t = i * kT + tid;
+                const int row = t >> 1, piece = t & 1, rot = row & 3;
+                const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(ql.qlut + static_cast<int64_t>(qi[0]) * 256 * M) + t);
+                const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(ql.qlut + static_cast<int64_t>(qi[1]) * 256 * M) + t);
+                uint4 e0, e1;
+                e0.x = __byte_perm(a0.x, a1.x, 0x5410);
+                e0.y = __byte_perm(a0.x, a1.x, 0x7632);
+                e0.z = __byte_perm(a0.y, a1.y, 0x5410);
+                e0.w = __byte_perm(a0.y, a1.y, 0x7632);
+                e1.x = __byte_perm(a0.z, a1.z, 0x5410);
+                e1.y = __byte_perm(a0.z, a1.z, 0x7632);
+                e1.z = __byte_perm(a0.w, a1.w, 0x5410);
+                e1.w = __byte_perm(a0.w, a1.w, 0x7632);
+                char* dst = lutb + row * 256 + piece * 32;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; s2++) {
+                    const int sp2 = (s2 + rot) & 3, cp = sp2 >> 1, jj = sp2 & 1;
+                    *reinterpret_cast<uint4*>(dst + cp * 64 + jj * 16) = jj ? e1 : e0;
+                }
+            }
+        } else
         {
             constexpr int kPieces = M / 8;            // 16-byte pieces per table row = pieces per thread
             constexpr int kBatch = 2;
@@ -685,6 +741,14 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
         }
 
         auto test = [&](const QlCode<M>& c) -> uint32_t {
+            if constexpr (TWO) {
+                const uint32_t lb = ql_block16_two(lutb, c.v[0], x8, x4, bsel, offs);
+                const float f0 = __uint_as_float(__byte_perm(lb, 0x4b000000u, 0x7410));
+                const float f1 = __uint_as_float(__byte_perm(lb, 0x4b000000u, 0x7432));
+                const float vs = static_cast<float>(c.s);
+                const bool h0 = !(f0 > fmaf(vs, na[0], tb[0])), h1 = !(f1 > fmaf(vs, na[1], tb[1]));
+                return (h0 ? 1u : 0u) | (h1 ? 2u : 0u);
+            }
             float f[4];
             ql_bounds_as_floats<M>(lutb, c.v, x8, x4, bsel, offs, f);
             const float vs = static_cast<float>(c.s);
@@ -720,6 +784,30 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
         };
 
         const uint32_t nblk = (n + kT - 1) / kT;
+        if constexpr (TWO) {
+#define ST_ITER2(SN, B)                                                                              \
+    {                                                                                                \
+        asm volatile("cp.async.wait_group 6;" ::: "memory");                                         \
+        QlCode<M> c;                                                                                 \
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"                                      \
+                     : "=r"(c.v[0].x), "=r"(c.v[0].y), "=r"(c.v[0].z), "=r"(c.v[0].w)                \
+                     : "r"(ring0 + ((B) & (kRing - 1)) * 8192u)                                      \
+                     : "memory");                                                                    \
+        c.s = SN;                                                                                    \
+        ring_issue((B) + kRing - 1);                                                                 \
+        SN = load_sn((B) + 2);                                                                       \
+        const uint32_t idx = (B) * kT + tid;                                                         \
+        const uint32_t m_ = test(c);                                                                 \
+        append(idx < n && m_ != 0u, (idx << 4) | m_);                                                \
+    }
+            static_assert(kRing == 8, "cp.async.wait_group 6 = kRing - 2");
+#pragma unroll 1
+            for (uint32_t b = 0; b < nblk; b += 2) {
+                ST_ITER2(snA, b)
+                if (b + 1 < nblk) ST_ITER2(snB, b + 1)
+            }
+#undef ST_ITER2
+        } else {
 #define ST_ITER(CUR, LOADTO, TB)                                                                     \
     {                                                                                                \
         LOADTO = ql_load_code<M>(lp, sp, base + (TB + 2) * kT, n);                                   \
@@ -736,6 +824,7 @@ st_filter_kernel(const ScanParams p, const QlParams ql, const StParams st) {
             if (t0 + 3 < nblk) ST_ITER(c3, c1, 3)
         }
 #undef ST_ITER
+        }
     }
     if (lane == 0) {
         if (chunk != 0xffffffffu) st.sfill[chunk] = fill;
@@ -1092,7 +1181,13 @@ st_eval_kernel(const ScanParams p, const StParams st) {
     const int stride = SMEM_PQ ? st_eval_row_stride(p.dsub) : p.dsub;
     const float* pq_rows = p.pq;
     if (SMEM_PQ) {
-        for (int e = tid; e < M * 256 * p.dsub; e += kStEvalThreads) st_spq[(e / p.dsub) * stride + e % p.dsub] = __ldg(p.pq + e);
+        if ((p.dsub & 3) == 0) {
+            const int v4 = p.dsub >> 2;
+            for (int e = tid; e < M * 256 * v4; e += kStEvalThreads)
+                *reinterpret_cast<float4*>(st_spq + (e / v4) * stride + 4 * (e % v4)) = __ldg(reinterpret_cast<const float4*>(p.pq) + e);
+        } else {
+            for (int e = tid; e < M * 256 * p.dsub; e += kStEvalThreads) st_spq[(e / p.dsub) * stride + e % p.dsub] = __ldg(p.pq + e);
+        }
         pq_rows = st_spq;
         __syncthreads();
     }

@@ -168,6 +168,7 @@ def test_qlut_filter_actually_filters(oracle):
     assert out[1] < 0.1 * codes, f"{out[1]} exact evaluations for {codes} (query, code) pairs: the filter is not filtering"
 
 
+@pytest.mark.parametrize("kind", ["1", "2"])
 @pytest.mark.parametrize("d,nlist,n,nq,nprobe,k,used", [
     (128, 24, 60000, 103, 5, 10, None),     # several tiles per list (ring of bulk-async tiles wraps), odd group sizes
     (96, 16, 12000, 64, 16, 100, 13),       # dsub 6, k = 100, empty lists
@@ -175,16 +176,17 @@ def test_qlut_filter_actually_filters(oracle):
     (128, 4, 9000, 200, 4, 1, None),        # k = 1, heavy ties
     (128, 6, 300, 20, 6, 10, None),         # lists shorter than one tile
 ])
-def test_two_query_filter_kernel(oracle, d, nlist, n, nq, nprobe, k, used):
-    """st_filter2_kernel (work items of two pairs, 32-bit table words, cp.async.bulk code tiles on an mbarrier ring),
-    forced for every batch; `auto` picks it when lists are probed by at most two queries on average."""
+def test_two_query_filter_kernel(oracle, d, nlist, n, nq, nprobe, k, used, kind):
+    """Work items of two pairs and 32-bit table words, forced for every batch.  kind 1: st_filter_kernel<16, true> (the
+    register-pipelined kernel `auto` picks when a list is probed by at most one query on average); kind 2:
+    st_filter2_kernel (cp.async.bulk code tiles on an mbarrier ring; opt-in experiment)."""
     a = _util.make_index_arrays(oracle, 290 + d, d, nlist, 16, n, used_lists=used)
     if nlist == 4:
         rng = np.random.default_rng(5)
         a["codes"] = np.ascontiguousarray(a["codes"][rng.integers(0, 500, size=a["codes"].shape[0])])
     xq = _util.make_queries(19, a, nq)
     Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
-    index = _load(a, env={"B200_IVFPQ_STREAM_TWO": "2"})
+    index = _load(a, env={"B200_IVFPQ_STREAM_TWO": kind, "B200_IVFPQ_SCAN": "qlut"})
     index.nprobe = nprobe
     for _ in range(3):
         D, I = index.search(xq, k)
