@@ -29,6 +29,7 @@ SYMBOLS = [
     ("b200_ivfpq_coarse_fallbacks", _I, [_P, ctypes.POINTER(_L)]),
     ("b200_ivfpq_search", _I, [_P, _L, _P, _I, _I, _P, _P, _P]),
     ("b200_ivfpq_search_preassigned", _I, [_P, _L, _P, _I, _I, _P, _P, _P, _P]),
+    ("b200_ivfpq_prepare_queries", _I, [_P, _L, _P, _P]),
     ("b200_ivfpq_search_preassigned_begin", _I, [_P, _L, _P, _I, _I, _P, _L, _L, _P, _P]),
     ("b200_ivfpq_search_preassigned_finish", _I, [_P, _P, _P, _P]),
     ("b200_ivfpq_search_host", _I, [_P, _L, _P, _I, _I, _P, _P]),

@@ -511,6 +511,19 @@ class IndexIVFPQ:
             return D, I
         return D.cpu().numpy(), I.cpu().numpy()
 
+    def prepare_queries(self, x: torch.Tensor) -> torch.Tensor:
+        """Optional head start for the next search of exactly these queries (b200_ivfpq_prepare_queries): their filter
+        tables are built on the handle's side stream while the caller still computes / exchanges the probe lists.
+        Returns the contiguous CUDA tensor to hand to that search; it must not be modified in between."""
+        dev = self._device()
+        h = self._sync_lists()
+        xq = x.contiguous()
+        if not (xq.is_cuda and xq.dtype == torch.float32 and xq.dim() == 2 and xq.shape[1] == self.d):
+            raise AssertionError("prepare_queries takes a (nq, d) float32 CUDA tensor")
+        with torch.cuda.device(dev):
+            _lib.check(h.lib.b200_ivfpq_prepare_queries(h.h, xq.shape[0], xq.data_ptr(), _stream_ptr(dev)))
+        return xq
+
     def search_preassigned_begin(self, x: torch.Tensor, k: int, list_ids: torch.Tensor, boot_lo: int, boot_hi: int):
         """First half of a sharded search (b200_ivfpq_search_preassigned_begin): returns the (nq,) int32 tensor of
         bootstrap-threshold bits (valid for the queries [boot_lo, boot_hi), +inf bits elsewhere), or None when the

@@ -285,6 +285,11 @@ class DistributedIndexIVFPQ:
         sliced = self.shard_coarse and self.world > 1 and nq >= 8 * self.world
         if not sliced and self.shard_mode == "vector":
             return self.local.search(xq, k, out=out) if out is not None else self.local.search(xq, k)
+        if sliced and self.shard_mode == "vector" and self.exchange_thresholds and hasattr(self.local, "prepare_queries") \
+                and isinstance(xq, torch.Tensor) and xq.is_cuda and xq.dtype == torch.float32:
+            # the filter tables depend on the queries only: they are built on a side stream while this rank's coarse
+            # slice and the probe exchange run
+            xq = self.local.prepare_queries(xq)
         if sliced:
             # coarse stage on my slice of the queries, then exchange the probe lists
             bounds = [(nq * r) // self.world for r in range(self.world + 1)]

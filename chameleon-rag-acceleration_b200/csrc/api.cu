@@ -122,6 +122,12 @@ struct b200_ivfpq_index {
         int k = 0, nprobe = 0, st_ctas = 0, ql_ctas = 0;
         cudaStream_t st = nullptr;
     } pend;
+    // b200_ivfpq_prepare_queries: the per-query tables of the NEXT search of (xq, nq) are already being built on `side`
+    struct Prepared {
+        bool valid = false;
+        const float* xq = nullptr;
+        int64_t nq = 0;
+    } prep;
     cudaStream_t side = nullptr;              // per-query tables overlap the coarse stage on this stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool side_ok() {
@@ -551,6 +557,10 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         if (ql_ctas) {
             quad_ctas = 0;
             if ((rc = ql_prepare(h, st))) return rc;
+            // (tables prepared ahead of this call live in these buffers: a reallocation drops them)
+            if (h->prep.valid && (h->ql_lut.cap < sizeof(uint16_t) * (size_t)qb * 256 * h->M || h->ql_scale.cap < sizeof(float) * qb ||
+                                  h->ql_amin.cap < sizeof(float) * qb))
+                h->prep.valid = false;
             if ((rc = h->ql_lut.ensure(sizeof(uint16_t) * (size_t)qb * 256 * h->M))) return rc;
             if ((rc = h->ql_scale.ensure(sizeof(float) * qb))) return rc;
             if ((rc = h->ql_amin.ensure(sizeof(float) * qb))) return rc;
@@ -566,7 +576,9 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
         // the per-query tables only need the queries: they are built on a side stream while the coarse quantizer and the
         // pair set-up run (not under stream capture: the latency path's CUDA graph keeps one stream)
         bool tables_async = false;
-        if (ql_ctas) {
+        if (ql_ctas && h->prep.valid && h->prep.xq == xq && h->prep.nq == nqc && nqc == nq) {
+            tables_async = true;      // b200_ivfpq_prepare_queries started them: ev_join is recorded
+        } else if (ql_ctas) {
             cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
             CUDA_TRY(cudaStreamIsCapturing(st, &cs));
             if (cs == cudaStreamCaptureStatusNone && h->side_ok()) {
@@ -581,6 +593,7 @@ int search_impl(b200_ivfpq_index* h, int64_t nq, const float* d_xq, int k, int n
             }
         }
 
+        h->prep.valid = false;        // one search per prepare
         if (tm) CUDA_TRY(cudaEventRecord(h->ev[0], st));
         if (d_list_ids) {
             probes_from_i64_kernel<<<grid1d(npairs, 256), 256, 0, st>>>(d_list_ids + q0 * nprobe, probe32, npairs,
@@ -895,6 +908,7 @@ int b200_ivfpq_set_codebooks(b200_ivfpq_t h, const float* d_centroids, const flo
     h->state_epoch++;
     h->ql_mu_ready = false;
     h->ql_index_ready = false;
+    h->prep.valid = false;
     {   // K1 tensor-core operands: B' = [ch | cl | ch] (nlist, kpad) bf16, ||c||^2, max ||c||^2
         CUDA_TRY(cudaSetDevice(h->device));
         h->tc_ready = false;
@@ -1127,6 +1141,37 @@ int search_host_small(b200_ivfpq_index* h, int64_t nq, const float* h_xq, int k,
 }
 
 }  // namespace
+
+extern "C" int b200_ivfpq_prepare_queries(b200_ivfpq_t h, int64_t nq, const float* d_xq, void* stream) {
+    if (!h) return fail(B200_IVFPQ_EINVAL, "null index handle");
+    if (nq <= 0 || !d_xq) return fail(B200_IVFPQ_EINVAL, "nq <= 0 or null queries");
+    h->prep.valid = false;
+    if (!h->cent || !h->pq || !h->has_lists) return 0;                      // the search call reports it
+    if (!(h->M == 16 || h->M == 32 || h->M == 64) || h->scan_variant == 6 || !h->st_mode) return 0;   // no per-query tables
+    if (nq > (int64_t(1) << 16)) return 0;                                  // larger batches are searched in chunks
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(st, &cs));
+    if (cs != cudaStreamCaptureStatusNone || !h->side_ok()) return 0;
+    int rc;
+    if ((rc = ql_prepare(h, st))) return rc;
+    // only into buffers a search has already sized: the first search of a handle builds its tables itself
+    if (h->ql_lut.cap < sizeof(uint16_t) * (size_t)nq * 256 * h->M || h->ql_scale.cap < sizeof(float) * nq ||
+        h->ql_amin.cap < sizeof(float) * nq)
+        return 0;
+    CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (ql_build_query_tables(d_xq, nq, h->pq, h->ql_mu.as<float>(), h->pq_maxnorm.as<float>(), h->d, h->M, h->dsub,
+                              h->ql_lut.as<uint16_t>(), h->ql_scale.as<float>(), h->ql_amin.as<float>(), h->side))
+        return fail(B200_IVFPQ_ECUDA, "query table launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
+    h->prep.valid = true;
+    h->prep.xq = d_xq;
+    h->prep.nq = nq;
+    return 0;
+}
 
 extern "C" int b200_ivfpq_search_preassigned_begin(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe,
                                                    const int64_t* d_list_ids, int64_t boot_lo, int64_t boot_hi,

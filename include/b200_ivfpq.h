@@ -95,6 +95,13 @@ B200_API int b200_ivfpq_search(b200_ivfpq_t h, int64_t nq, const float* d_xq, in
 B200_API int b200_ivfpq_search_preassigned(b200_ivfpq_t h, int64_t nq, const float* d_xq, int k, int nprobe,
                                   const int64_t* d_list_ids, float* d_D, int64_t* d_I, void* stream);
 
+/* Optional head start for the NEXT search of exactly (nq, d_xq) on this handle: the per-query tables the scan filters
+ * with depend on the queries only, so they can be built (on the handle's own side stream, ordered after `stream`) while
+ * the caller still computes or exchanges the probe lists -- the sharded search of bench_gpu_performance_OSDI.py:586-604
+ * runs the coarse quantizer on a slice of the batch and all-gathers the probes first.  The queries must not change
+ * between this call and the search.  A no-op (return 0) wherever it does not apply; results never depend on it. */
+B200_API int b200_ivfpq_prepare_queries(b200_ivfpq_t h, int64_t nq, const float* d_xq, void* stream);
+
 /* The same search in two halves, for an index sharded by vector over several GPUs (bench_gpu_performance_OSDI.py:586-604,
  * co.shard = True).  Every shard needs, per query, an upper bound on the FINAL k-th distance before it filters its codes;
  * any shard's own k-th best distance is one.  _begin does everything up to those bootstrap thresholds, but only for the

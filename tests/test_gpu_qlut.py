@@ -194,6 +194,35 @@ def test_two_query_filter_kernel(oracle, d, nlist, n, nq, nprobe, k, used, kind)
         _util.assert_bit_equal(I, Ir, "I (two-query filter)")
 
 
+def test_prepared_query_tables(oracle):
+    """b200_ivfpq_prepare_queries: tables built ahead of the search (same queries) give the oracle's result; a prepare for
+    OTHER queries is ignored; a prepare before the first search of a handle (buffers not sized yet) is a no-op."""
+    import torch
+    a, xq = _scaled(oracle, 33, 128, 16, 16, 50000, 96, 1.0, 0.0)
+    nprobe, k, nq = 6, 10, xq.shape[0]
+    Dr, Ir = oracle.C.search(xq, a["coarse"], a["pq"], a["offsets"], a["codes"], a["ids"], nprobe, k)
+    index = _load(a)
+    index.nprobe = nprobe
+    xq_t = torch.from_numpy(xq).cuda()
+    other = torch.flip(xq_t, dims=(0,)).contiguous()
+    for step in range(4):
+        held = index.prepare_queries(xq_t if step != 2 else other)      # step 0: before the first search
+        _, probes = index.quantizer.search(xq_t, nprobe)
+        if step == 3:
+            D, I = index.search_preassigned(held, k, probes)
+        else:
+            thr = index.search_preassigned_begin(xq_t if step == 2 else held, k, probes, 0, nq)
+            assert thr is not None
+            D, I = index.search_preassigned_finish(thr, nq, k)
+        _util.assert_bit_equal(D.cpu().numpy(), Dr, f"D (prepared tables, step {step})")
+        _util.assert_bit_equal(I.cpu().numpy(), Ir, f"I (prepared tables, step {step})")
+    # and the plain search right after a prepare of the same tensor
+    held = index.prepare_queries(xq_t)
+    D, I = index.search(held, k)
+    _util.assert_bit_equal(D.cpu().numpy(), Dr, "D (prepared, full search)")
+    _util.assert_bit_equal(I.cpu().numpy(), Ir, "I (prepared, full search)")
+
+
 def test_split_search_begin_finish(oracle):
     """b200_ivfpq_search_preassigned_begin / _finish (the multi-GPU threshold exchange) on one GPU: thresholds of all
     queries, of half of them (the other half then has none: everything survives, the buffers overflow, the fallback
