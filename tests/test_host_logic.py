@@ -242,6 +242,21 @@ def test_sass_is_blackwell_native_and_exact():
     for kern in ("coarse_dist_kernel", "encode_kernel", "coarse_exact_flagged_kernel"):
         _, text = ops(kern)
         assert not re.search(r"\bFFMA\b", text), f"contracted FFMA in {kern}"
+    # round 2's filter kernels (csrc/scan_stream.cuh).  Four queries: 16 LDS.64 look-ups per code and unrolled block,
+    # the table copy with 128-bit loads / stores, no fp32 multiply on the code path besides the one FFMA per
+    # (code, query) of the threshold test, no local memory.  Two queries: the look-ups are 32-bit, the codes arrive by
+    # LDGSTS (cp.async) and come back with one LDS.128 per code.  The bulk-async experiment keeps UBLKCP + SYNCS.
+    four = "\n".join(funcs[[n for n in funcs if "st_filter_kernelILi16ELb0E" in n][0]])
+    assert four.count("LDS.64") >= 16 * 4 and four.count("STS.128") >= 8 and "LDGSTS" in four   # (group descriptor)
+    assert not re.search(r"\b(LDL|STL)\b", four), "the filter kernel spills"
+    two = "\n".join(funcs[[n for n in funcs if "st_filter_kernelILi16ELb1E" in n][0]])
+    assert len(re.findall(r"\bLDS R", two)) >= 16 * 2, "32-bit look-ups"
+    assert two.count("LDS.64") < 16 and two.count("LDGSTS.E.BYPASS.128") >= 7 + 2 and two.count("LDS.128") >= 2
+    assert not re.search(r"\b(LDL|STL)\b", two), "the two-query filter kernel spills"
+    _, bulk = ops("st_filter2_kernel")
+    assert "UBLKCP" in bulk and "SYNCS" in bulk
+    evals = "\n".join(funcs[[n for n in funcs if "st_eval_kernelILi16ELb1E" in n][0]])
+    assert evals.count("LDS.128") >= 2, "codebook rows gathered from shared memory"
 
 
 def test_faiss_named_shims():
